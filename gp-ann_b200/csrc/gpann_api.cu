@@ -1,0 +1,864 @@
+// gpann_api.cu -- the C ABI of libgpann_cuda.so (declared in include/gpann.h) over the sm_100a kernels.
+// No CPU fallback lives here: every compute entry point launches CUDA kernels or fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gpann.h"
+#include "common.cuh"
+#include "kmeans.cuh"
+#include "prep.cuh"
+#include "stream.cuh"
+#include "topk_tc.cuh"
+
+using namespace gpann;
+
+// ---- handles ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct gpann_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int algo = GPANN_ALGO_AUTO;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    const char* last_algo = "none";
+    EncodeTiledFn encode_tiled = nullptr;
+    int tc_mode = 0;  // GPANN_TC_MODE env: 1 = roofline probe (MMA + TMEM loads only)
+    // grow-only scratch, reused across calls (a ctx is externally synchronised)
+    DevBuf partial, cand, qrows, qnorm, flags, keys_out, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b,
+        sort_c, sort_d, segsums, cent, sums, counts, assign;
+};
+
+struct gpann_points {
+    gpann_ctx* ctx = nullptr;
+    size_t n = 0, d = 0;
+    int storage = GPANN_STORAGE_F32;
+    uint32_t id_base = 0;
+    // rows in original order: float [n,d] or bytes [n,d]
+    void* rows = nullptr;
+    size_t pitch = 0;
+    bool owns_rows = true;
+    // norm-sorted tensor layout for byte storage with d <= 128 (topk_tc.cuh)
+    unsigned char* t_rows = nullptr;
+    int32_t* t_norms = nullptr;
+    uint32_t* t_ids = nullptr;
+    size_t n_pad = 0;
+    CUtensorMap tmap;
+    bool has_tensor = false;
+};
+
+namespace {
+
+int fail(gpann_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                                      \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? GPANN_E_OOM : GPANN_E_CUDA,                    \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                                  \
+        }                                                                                                      \
+    } while (0)
+
+#define GP_TRY(expr)             \
+    do {                         \
+        int r__ = (expr);        \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+int reserve(gpann_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = std::max(bytes, (size_t) 256);
+    CU_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int odd16_pitch(int row_bytes) {
+    int p = (row_bytes + 15) & ~15;
+    if (((p >> 4) & 1) == 0) p += 16;
+    return p;
+}
+
+int check_launch(gpann_ctx* ctx, const char* what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, GPANN_E_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return 0;
+}
+
+int log2_ceil(size_t x) {
+    int b = 0;
+    while (((size_t) 1 << b) < x) ++b;
+    return b;
+}
+
+// ---- tensor layout for byte rows ---------------------------------------------------------------------------
+int build_tensor_bytes(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
+    const size_t n = pts->n;
+    const int d = (int) pts->d;
+    if (n == 0 || d > tc::kRowBytes || n > 0xFFFFFF00ull) return 0;
+    if (!ctx->encode_tiled) return 0;
+    const size_t n_pad = ((n + tc::kTileN - 1) / tc::kTileN) * tc::kTileN;
+    uint32_t *norms = nullptr, *index = nullptr, *norms_sorted = nullptr, *perm = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    auto cleanup = [&]() {
+        cudaFree(norms); cudaFree(index); cudaFree(norms_sorted); cudaFree(perm); cudaFree(tmp);
+    };
+    CU_TRY(ctx, cudaMalloc(&norms, n * 4));
+    if (cudaMalloc(&index, n * 4) != cudaSuccess || cudaMalloc(&norms_sorted, n * 4) != cudaSuccess ||
+        cudaMalloc(&perm, n * 4) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory");
+    }
+    const int is_signed = pts->storage == GPANN_STORAGE_S8;
+    const int blocks = (int) std::min<size_t>((n + 255) / 256, (size_t) ctx->num_sms * 16);
+    byte_norms_kernel<<<blocks, 256, 0, st>>>((const unsigned char*) pts->rows, n, d, pts->pitch, is_signed, norms, index);
+    GP_TRY(check_launch(ctx, "byte_norms_kernel"));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, norms, norms_sorted, index, perm, (int) n, 0, 25, st);
+    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (sort)");
+    }
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, norms, norms_sorted, index, perm, (int) n, 0, 25, st);
+    ctx->launches += 4;
+    if (cudaMalloc(&pts->t_rows, n_pad * tc::kRowBytes) != cudaSuccess || cudaMalloc(&pts->t_norms, n_pad * 4) != cudaSuccess ||
+        cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (layout)");
+    }
+    const int gblocks = (int) std::min<size_t>((n_pad * 32 + 255) / 256, (size_t) ctx->num_sms * 32);
+    gather_sorted_rows_kernel<<<gblocks, 256, 0, st>>>((const unsigned char*) pts->rows, n, d, pts->pitch, perm, norms_sorted,
+                                                       pts->id_base, n_pad, pts->t_rows, pts->t_norms, pts->t_ids);
+    GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    cleanup();
+    pts->n_pad = n_pad;
+    const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) n_pad };
+    const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
+    const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) tc::kTileN };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = ctx->encode_tiled(&pts->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, pts->t_rows, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GPANN_E_CUDA, "cuTensorMapEncodeTiled(points) failed: " + std::to_string((int) r));
+    pts->has_tensor = true;
+    return 0;
+}
+
+// ---- top-k dispatch ----------------------------------------------------------------------------------------
+struct TopkOut {
+    uint64_t* keys = nullptr;  // device [nq,k]
+    float* dist = nullptr;     // device [nq,k]
+    uint32_t* id = nullptr;    // device [nq,k]
+    uint32_t* count = nullptr; // device [nq]
+    float* kth = nullptr;      // device [nq]
+};
+
+int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_stride, size_t q_offset, size_t nq, int k,
+                 const TopkOut& o, size_t out_q_offset, cudaStream_t st) {
+    MergeParams mp;
+    mp.keys = keys + q_offset * k;
+    mp.parts = parts;
+    mp.nq = nq;
+    mp.nq_stride = nq_stride;
+    mp.k = k;
+    mp.cap = std::max(64, pow2_ceil(2 * k));
+    mp.out_dist = o.dist ? o.dist + out_q_offset * k : nullptr;
+    mp.out_id = o.id ? o.id + out_q_offset * k : nullptr;
+    mp.out_keys = o.keys ? o.keys + out_q_offset * k : nullptr;
+    mp.out_count = o.count ? o.count + out_q_offset : nullptr;
+    mp.out_kth = o.kth ? o.kth + out_q_offset : nullptr;
+    const size_t smem = (size_t) 4 * mp.cap * sizeof(uint64_t);
+    merge_keys_kernel<<<(unsigned) ((nq + 3) / 4), 128, smem, st>>>(mp);
+    return check_launch(ctx, "merge_keys_kernel");
+}
+
+template <int STORAGE>
+int launch_stream_t(gpann_ctx* ctx, const StreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    topk_stream_kernel<STORAGE><<<grid, kStreamTile, smem, st>>>(p);
+    return check_launch(ctx, "topk_stream_kernel");
+}
+
+int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
+                int metric, const TopkOut& out, cudaStream_t st) {
+    StreamParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.rows = (const char*) pts->rows;
+    p.pitch = pts->pitch;
+    p.storage = pts->storage;
+    p.d = (int) pts->d;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    p.ids = nullptr;
+    p.id_base = pts->id_base;
+    p.id_lo = 0;
+    p.id_hi = 0xFFFFFFFFu;
+    p.queries = dq;
+    p.nq = (int) nq;
+    p.k = k;
+    p.metric = metric;
+    const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
+    const int row_bytes = p.d * elem;
+    p.spitch = odd16_pitch(row_bytes);
+    p.qpitch = (p.d + 3) & ~3;
+    p.cap = pow2_ceil(k + kStreamTile);
+    p.vec_ok = (((uintptr_t) pts->rows + row_begin * pts->pitch) % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
+    const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
+    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16;
+    const size_t budget = 160 * 1024;
+    if (tile_bytes + per_q > 200 * 1024)
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile");
+    int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16), std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
+    p.qb = qb;
+    const size_t smem = tile_bytes + (size_t) qb * per_q;
+    const size_t nrows = row_end - row_begin;
+    const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
+    const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const unsigned gx = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
+    const unsigned gy = (unsigned) ((nq + qb - 1) / qb);
+    GP_TRY(reserve(ctx, ctx->partial, (size_t) gx * nq * k * sizeof(uint64_t)));
+    p.partial = (uint64_t*) ctx->partial.p;
+    int r;
+    if (pts->storage == GPANN_STORAGE_F32) r = launch_stream_t<kF32>(ctx, p, dim3(gx, gy), smem, st);
+    else if (pts->storage == GPANN_STORAGE_U8) r = launch_stream_t<kU8>(ctx, p, dim3(gx, gy), smem, st);
+    else r = launch_stream_t<kS8>(ctx, p, dim3(gx, gy), smem, st);
+    GP_TRY(r);
+    ctx->last_algo = "stream";
+    return launch_merge(ctx, p.partial, gx, nq, 0, nq, k, out, 0, st);
+}
+
+int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
+                      cudaStream_t st, int* queries_ok_host) {
+    const int is_signed = pts->storage == GPANN_STORAGE_S8;
+    const int d = (int) pts->d;
+    const size_t batch_max = (size_t) ctx->num_sms * tc::kMaxR * tc::kTileM;
+    *queries_ok_host = 1;
+    for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
+        const size_t nqb = std::min(batch_max, nq - q0);
+        const int R = (int) std::min<size_t>(tc::kMaxR, (nqb + tc::kTileM - 1) / tc::kTileM);
+        const int G = (int) ((nqb + (size_t) R * tc::kTileM - 1) / ((size_t) R * tc::kTileM));
+        const uint32_t tiles_total = (uint32_t) (pts->n_pad / tc::kTileN);
+        const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / G), tiles_total));
+        const size_t nq_pad = (size_t) G * R * tc::kTileM;
+        const int cap = std::max(128, pow2_ceil(k + 64));
+        GP_TRY(reserve(ctx, ctx->qrows, nq_pad * tc::kRowBytes));
+        GP_TRY(reserve(ctx, ctx->qnorm, nq_pad * 4));
+        GP_TRY(reserve(ctx, ctx->flags, 64));
+        GP_TRY(reserve(ctx, ctx->cand, (size_t) G * S * R * tc::kTileM * cap * sizeof(uint64_t)));
+        GP_TRY(reserve(ctx, ctx->partial, (size_t) S * nq_pad * k * sizeof(uint64_t)));
+        int one = 1;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
+        prep_queries_bytes_kernel<<<(unsigned) std::min<size_t>((nq_pad * 32 + 255) / 256, 1024), 256, 0, st>>>(
+            dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p, (int32_t*) ctx->qnorm.p,
+            (int*) ctx->flags.p);
+        GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
+        int ok = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&ok, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        if (!ok) {
+            *queries_ok_host = 0;
+            return 0;
+        }
+        CUtensorMap tmap_q;
+        const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) nq_pad };
+        const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
+        const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) tc::kTileM };
+        const cuuint32_t estr[2] = { 1, 1 };
+        CUresult cr = ctx->encode_tiled(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->qrows.p, gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(ctx, GPANN_E_CUDA, "cuTensorMapEncodeTiled(queries) failed: " + std::to_string((int) cr));
+        tc::Args a;
+        a.pnorm = pts->t_norms;
+        a.pid = pts->t_ids;
+        a.qnorm = (const int32_t*) ctx->qnorm.p;
+        a.R = R;
+        a.G = G;
+        a.S = S;
+        a.nks = (d + 31) / 32;
+        a.k = k;
+        a.cap = cap;
+        a.tiles_total = tiles_total;
+        a.idesc = tc::make_idesc_i8(is_signed);
+        a.cand = (uint64_t*) ctx->cand.p;
+        a.partial = (uint64_t*) ctx->partial.p;
+        a.mode = ctx->tc_mode;
+        tc::topk_tc_bytes_kernel<<<G * S, tc::kThreads, tc::smem_bytes(R), st>>>(pts->tmap, tmap_q, a);
+        GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel"));
+        GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, 0, nqb, k, out, q0, st));
+    }
+    ctx->last_algo = pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8";
+    return 0;
+}
+
+int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
+                  int metric, const TopkOut& out, cudaStream_t st) {
+    if (!pts || pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "topk: point set does not belong to this context");
+    if (k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "topk: k must be in [1,512]");
+    if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(ctx, GPANN_E_ARG, "topk: bad metric");
+    if (row_begin > row_end || row_end > pts->n) return fail(ctx, GPANN_E_ARG, "topk: bad row range");
+    if (nq == 0) return 0;
+    const bool full = row_begin == 0 && row_end == pts->n;
+    const bool tensor_ok = pts->has_tensor && metric == GPANN_METRIC_L2 && full && k <= 448;
+    if (ctx->algo == GPANN_ALGO_TENSOR && !tensor_ok)
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs byte storage with d<=128, L2, full range, k<=448");
+    if (tensor_ok && (ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16))) {
+        int ok = 1;
+        GP_TRY(topk_tensor_bytes(ctx, pts, dq, nq, k, out, st, &ok));
+        if (ok) return 0;
+        if (ctx->algo == GPANN_ALGO_TENSOR)
+            return fail(ctx, GPANN_E_UNSUPPORTED, "topk: queries are not integer-valued in the storage range");
+    }
+    if (row_end == row_begin) {
+        // empty scan: all-empty output
+        std::vector<uint64_t> e(nq * k, kEmptyKey);
+        GP_TRY(reserve(ctx, ctx->partial, e.size() * 8));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->partial.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->last_algo = "empty";
+        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, nq, 0, nq, k, out, 0, st);
+    }
+    return topk_stream(ctx, pts, row_begin, row_end, dq, nq, k, metric, out, st);
+}
+
+int topk_host(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries, size_t nq, int k,
+              int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count, float* out_kth) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !queries) return fail(ctx, GPANN_E_ARG, "topk: null argument");
+    if (nq == 0) return 0;
+    if (k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "topk: k must be in [1,512]");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t d = pts->d;
+    GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
+    GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->id_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->cnt_out, nq * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdev.p, queries, nq * d * 4, cudaMemcpyHostToDevice, st));
+    TopkOut o;
+    o.dist = out_dist ? (float*) ctx->dist_out.p : nullptr;
+    o.id = out_id ? (uint32_t*) ctx->id_out.p : nullptr;
+    o.count = out_count ? (uint32_t*) ctx->cnt_out.p : nullptr;
+    o.kth = out_kth ? (float*) ctx->cnt_out.p + nq : nullptr;
+    GP_TRY(topk_dispatch(ctx, pts, row_begin, row_end, (const float*) ctx->qdev.p, nq, k, metric, o, st));
+    if (out_dist) CU_TRY(ctx, cudaMemcpyAsync(out_dist, o.dist, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_id) CU_TRY(ctx, cudaMemcpyAsync(out_id, o.id, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_count) CU_TRY(ctx, cudaMemcpyAsync(out_count, o.count, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (out_kth) CU_TRY(ctx, cudaMemcpyAsync(out_kth, o.kth, nq * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- k-means helpers -----------------------------------------------------------------------------------------
+RowsView rows_view(const gpann_points* pts) {
+    RowsView v;
+    v.rows = (const char*) pts->rows;
+    v.pitch = pts->pitch;
+    v.storage = pts->storage;
+    v.d = (int) pts->d;
+    v.n = pts->n;
+    v.ids = nullptr;
+    v.id_base = 0;
+    return v;
+}
+
+template <int STORAGE>
+int launch_assign_t(gpann_ctx* ctx, const AssignParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+    kmeans_assign_kernel<STORAGE><<<grid, kStreamTile, smem, st>>>(p);
+    return check_launch(ctx, "kmeans_assign_kernel");
+}
+
+int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric,
+                         int32_t* d_assign, float* d_mindist, cudaStream_t st) {
+    AssignParams p;
+    p.pts = rows_view(pts);
+    p.centroids = d_centroids;
+    p.kc = (int) kc;
+    p.metric = metric;
+    const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
+    const int row_bytes = (int) pts->d * elem;
+    p.spitch = odd16_pitch(row_bytes);
+    p.qpitch = ((int) pts->d + 3) & ~3;
+    p.vec_ok = ((uintptr_t) pts->rows % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
+    const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
+    const size_t per_c = (size_t) p.qpitch * 4;
+    if (tile_bytes + per_c > 200 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: d too large");
+    const size_t budget = std::max<size_t>(tile_bytes + per_c, 100 * 1024);
+    p.cchunk = (int) std::max<size_t>(1, std::min<size_t>(kc, (budget - tile_bytes) / per_c));
+    p.out_assign = d_assign;
+    p.out_mindist = d_mindist;
+    const size_t smem = tile_bytes + (size_t) p.cchunk * per_c;
+    const size_t ntiles = (pts->n + kStreamTile - 1) / kStreamTile;
+    const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
+    if (pts->storage == GPANN_STORAGE_F32) return launch_assign_t<kF32>(ctx, p, grid, smem, st);
+    if (pts->storage == GPANN_STORAGE_U8) return launch_assign_t<kU8>(ctx, p, grid, smem, st);
+    return launch_assign_t<kS8>(ctx, p, grid, smem, st);
+}
+
+// sums [kc,d] (optionally normalised) and counts [kc] of the points assigned to each cluster, fixed order.
+int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* d_assign, size_t kc, int normalize,
+                        float* d_out, uint64_t* d_counts, cudaStream_t st) {
+    const size_t n = pts->n;
+    const int d = (int) pts->d;
+    if (n > 0x7FFFFFFFull) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: n must be below 2^31 per device");
+    CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, kc * 8, st));
+    GP_TRY(reserve(ctx, ctx->sort_a, n * 4));
+    GP_TRY(reserve(ctx, ctx->sort_b, n * 4));
+    GP_TRY(reserve(ctx, ctx->sort_c, n * 4));
+    GP_TRY(reserve(ctx, ctx->sort_d, n * 4));
+    uint32_t* keys_in = (uint32_t*) ctx->sort_a.p;
+    uint32_t* keys_out = (uint32_t*) ctx->sort_b.p;
+    uint32_t* idx_in = (uint32_t*) ctx->sort_c.p;
+    uint32_t* idx_out = (uint32_t*) ctx->sort_d.p;
+    const int blocks = (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t) ctx->num_sms * 16));
+    histogram_keys_kernel<<<blocks, 256, 0, st>>>(d_assign, n, (int) kc, (unsigned long long*) d_counts, keys_in, idx_in);
+    GP_TRY(check_launch(ctx, "histogram_keys_kernel"));
+    const int bits = std::max(1, log2_ceil(kc + 1));
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, idx_in, idx_out, (int) n, 0, bits, st);
+    GP_TRY(reserve(ctx, ctx->sort_tmp, tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, keys_in, keys_out, idx_in, idx_out, (int) n, 0, bits, st);
+    ctx->launches += 3;
+    GP_TRY(reserve(ctx, ctx->misc, (kc + 1) * 4 + (kc + 1) * 8 + 64));
+    uint64_t* member_begin = (uint64_t*) ctx->misc.p;
+    uint32_t* seg_begin = (uint32_t*) (member_begin + kc + 1);
+    cluster_segments_kernel<<<1, 32, 0, st>>>(d_counts, (int) kc, seg_begin, member_begin);
+    GP_TRY(check_launch(ctx, "cluster_segments_kernel"));
+    const size_t max_segs = n / kSegRows + kc + 1;
+    GP_TRY(reserve(ctx, ctx->segsums, max_segs * d * 4));
+    ReduceParams rp;
+    rp.pts = rows_view(pts);
+    rp.members = idx_out;
+    rp.seg_begin = seg_begin;
+    rp.member_begin = member_begin;
+    rp.kc = (int) kc;
+    rp.seg_sums = (float*) ctx->segsums.p;
+    if (pts->storage == GPANN_STORAGE_F32) cluster_reduce_segments_kernel<kF32><<<(unsigned) max_segs, 256, 0, st>>>(rp);
+    else if (pts->storage == GPANN_STORAGE_U8) cluster_reduce_segments_kernel<kU8><<<(unsigned) max_segs, 256, 0, st>>>(rp);
+    else cluster_reduce_segments_kernel<kS8><<<(unsigned) max_segs, 256, 0, st>>>(rp);
+    GP_TRY(check_launch(ctx, "cluster_reduce_segments_kernel"));
+    cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(rp.seg_sums, seg_begin, d_counts, (int) kc, d, normalize, d_out);
+    return check_launch(ctx, "cluster_finalize_kernel");
+}
+
+}  // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpann_init(gpann_ctx** out, int device) {
+    if (!out) return GPANN_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return GPANN_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return GPANN_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPANN_E_CUDA;
+    if (prop.major != 10) {
+        std::fprintf(stderr, "gpann_init: device %d is sm_%d%d; libgpann_cuda is built for sm_100a only\n", device, prop.major,
+                     prop.minor);
+        return GPANN_E_UNSUPPORTED;
+    }
+    gpann_ctx* ctx = new (std::nothrow) gpann_ctx();
+    if (!ctx) return GPANN_E_OOM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GPANN_E_CUDA;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        ctx->encode_tiled = (EncodeTiledFn) fn;
+    {
+        // opt every large-shared-memory kernel in for this device (attributes are per device)
+        const int big = 200 * 1024;
+        bool ok = true;
+        ok &= cudaFuncSetAttribute(topk_stream_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(topk_stream_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(topk_stream_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(objective_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(objective_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(objective_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(tc::topk_tc_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) tc::smem_bytes(tc::kMaxR)) == cudaSuccess;
+        if (!ok) {
+            std::fprintf(stderr, "gpann_init: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return GPANN_E_CUDA;
+        }
+    }
+    const char* mode = std::getenv("GPANN_TC_MODE");
+    ctx->tc_mode = mode ? std::atoi(mode) : 0;
+    *out = ctx;
+    return 0;
+}
+
+void gpann_destroy(gpann_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->flags, &ctx->keys_out, &ctx->dist_out,
+                       &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
+                       &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign };
+    for (DevBuf* b : bufs) release(*b);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* gpann_last_error(const gpann_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int gpann_device(const gpann_ctx* ctx) { return ctx ? ctx->device : -1; }
+int gpann_set_algo(gpann_ctx* ctx, int algo) {
+    if (!ctx || algo < GPANN_ALGO_AUTO || algo > GPANN_ALGO_TENSOR) return GPANN_E_ARG;
+    ctx->algo = algo;
+    return 0;
+}
+uint64_t gpann_launch_count(const gpann_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* gpann_last_algo(const gpann_ctx* ctx) { return ctx ? ctx->last_algo : "none"; }
+
+static int finish_points(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st, gpann_points** out) {
+    if (pts->storage != GPANN_STORAGE_F32) {
+        int r = build_tensor_bytes(ctx, pts, st);
+        if (r != 0) {
+            gpann_points_free(pts);
+            return r;
+        }
+    }
+    *out = pts;
+    return 0;
+}
+
+int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base,
+                        gpann_points** out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!out || (!host_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_upload: bad argument");
+    if (storage < GPANN_STORAGE_AUTO || storage > GPANN_STORAGE_S8) return fail(ctx, GPANN_E_ARG, "points_upload: bad storage");
+    if ((uint64_t) id_base + n > 0xFFFFFFFFull) return fail(ctx, GPANN_E_ARG, "points_upload: ids exceed 32 bits (recall.h:30)");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    *out = nullptr;
+    cudaStream_t st = ctx->stream;
+    float* d_f32 = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d_f32, std::max<size_t>(n * d * 4, 256)));
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(d_f32, host_rows, n * d * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            cudaFree(d_f32);
+            return fail(ctx, GPANN_E_CUDA, std::string("points_upload H2D: ") + cudaGetErrorString(e));
+        }
+    }
+    if (storage == GPANN_STORAGE_AUTO && n) {
+        int flags_h[2] = { 1, 1 };
+        GP_TRY(reserve(ctx, ctx->flags, 64));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, flags_h, 8, cudaMemcpyHostToDevice, st));
+        const int blocks = (int) std::min<size_t>((n * d + 255) / 256, (size_t) ctx->num_sms * 16);
+        detect_bytes_kernel<<<blocks, 256, 0, st>>>(d_f32, n * d, (int*) ctx->flags.p);
+        GP_TRY(check_launch(ctx, "detect_bytes_kernel"));
+        CU_TRY(ctx, cudaMemcpyAsync(flags_h, ctx->flags.p, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        storage = flags_h[0] ? GPANN_STORAGE_U8 : (flags_h[1] ? GPANN_STORAGE_S8 : GPANN_STORAGE_F32);
+    } else if (storage == GPANN_STORAGE_AUTO) {
+        storage = GPANN_STORAGE_F32;
+    }
+    gpann_points* pts = new (std::nothrow) gpann_points();
+    if (!pts) {
+        cudaFree(d_f32);
+        return fail(ctx, GPANN_E_OOM, "points_upload: host allocation failed");
+    }
+    pts->ctx = ctx;
+    pts->n = n;
+    pts->d = d;
+    pts->storage = storage;
+    pts->id_base = id_base;
+    if (storage == GPANN_STORAGE_F32) {
+        pts->rows = d_f32;
+        pts->pitch = d * 4;
+    } else {
+        unsigned char* bytes = nullptr;
+        cudaError_t e = cudaMalloc(&bytes, std::max<size_t>(n * d, 256));
+        if (e != cudaSuccess) {
+            cudaFree(d_f32);
+            delete pts;
+            return fail(ctx, GPANN_E_OOM, "points_upload: out of device memory");
+        }
+        if (n) {
+            const int blocks = (int) std::min<size_t>((n * d + 255) / 256, (size_t) ctx->num_sms * 16);
+            narrow_rows_kernel<<<blocks, 256, 0, st>>>(d_f32, n, (int) d, (int) d, bytes);
+            ctx->launches++;
+        }
+        cudaStreamSynchronize(st);
+        cudaFree(d_f32);
+        pts->rows = bytes;
+        pts->pitch = d;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return finish_points(ctx, pts, st, out);
+}
+
+int gpann_points_upload_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                              gpann_points** out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!out || (!host_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_upload_bytes: bad argument");
+    if ((uint64_t) id_base + n > 0xFFFFFFFFull) return fail(ctx, GPANN_E_ARG, "points_upload_bytes: ids exceed 32 bits");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    *out = nullptr;
+    unsigned char* bytes = nullptr;
+    CU_TRY(ctx, cudaMalloc(&bytes, std::max<size_t>(n * d, 256)));
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(bytes, host_rows, n * d, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(bytes);
+            return fail(ctx, GPANN_E_CUDA, std::string("points_upload_bytes H2D: ") + cudaGetErrorString(e));
+        }
+    }
+    gpann_points* pts = new (std::nothrow) gpann_points();
+    if (!pts) {
+        cudaFree(bytes);
+        return fail(ctx, GPANN_E_OOM, "points_upload_bytes: host allocation failed");
+    }
+    pts->ctx = ctx;
+    pts->n = n;
+    pts->d = d;
+    pts->storage = is_signed ? GPANN_STORAGE_S8 : GPANN_STORAGE_U8;
+    pts->id_base = id_base;
+    pts->rows = bytes;
+    pts->pitch = d;
+    return finish_points(ctx, pts, ctx->stream, out);
+}
+
+int gpann_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, size_t d, int storage, uint32_t id_base, void* stream,
+                             gpann_points** out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!out || (!dev_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_from_device: bad argument");
+    if (storage < GPANN_STORAGE_F32 || storage > GPANN_STORAGE_S8) return fail(ctx, GPANN_E_ARG, "points_from_device: bad storage");
+    if ((uint64_t) id_base + n > 0xFFFFFFFFull) return fail(ctx, GPANN_E_ARG, "points_from_device: ids exceed 32 bits");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    *out = nullptr;
+    gpann_points* pts = new (std::nothrow) gpann_points();
+    if (!pts) return fail(ctx, GPANN_E_OOM, "points_from_device: host allocation failed");
+    pts->ctx = ctx;
+    pts->n = n;
+    pts->d = d;
+    pts->storage = storage;
+    pts->id_base = id_base;
+    pts->rows = const_cast<void*>(dev_rows);  // borrowed: the caller keeps the rows alive
+    pts->owns_rows = false;
+    pts->pitch = storage == GPANN_STORAGE_F32 ? d * 4 : d;
+    return finish_points(ctx, pts, stream ? (cudaStream_t) stream : ctx->stream, out);
+}
+
+void gpann_points_free(gpann_points* pts) {
+    if (!pts) return;
+    if (pts->ctx) cudaSetDevice(pts->ctx->device);
+    if (pts->owns_rows && pts->rows) cudaFree(pts->rows);
+    if (pts->t_rows) cudaFree(pts->t_rows);
+    if (pts->t_norms) cudaFree(pts->t_norms);
+    if (pts->t_ids) cudaFree(pts->t_ids);
+    delete pts;
+}
+size_t gpann_points_n(const gpann_points* pts) { return pts ? pts->n : 0; }
+size_t gpann_points_d(const gpann_points* pts) { return pts ? pts->d : 0; }
+int gpann_points_storage(const gpann_points* pts) { return pts ? pts->storage : 0; }
+
+int gpann_topk(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric, float* out_dist,
+               uint32_t* out_id, uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts) return fail(ctx, GPANN_E_ARG, "topk: null point set");
+    return topk_host(ctx, pts, 0, pts->n, queries, nq, k, metric, out_dist, out_id, out_count, nullptr);
+}
+
+int gpann_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
+                       float* out_kth) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !out_kth) return fail(ctx, GPANN_E_ARG, "kth_distance: null argument");
+    return topk_host(ctx, pts, 0, pts->n, queries, nq, k, metric, nullptr, nullptr, nullptr, out_kth);
+}
+
+int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries, size_t nq,
+                     int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts) return fail(ctx, GPANN_E_ARG, "topk_range: null point set");
+    return topk_host(ctx, pts, row_begin, row_end, queries, nq, k, metric, out_dist, out_id, out_count, nullptr);
+}
+
+int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
+                      uint64_t* dev_out_keys, void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !dev_queries || !dev_out_keys) return fail(ctx, GPANN_E_ARG, "topk_device: null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    TopkOut o;
+    o.keys = dev_out_keys;
+    return topk_dispatch(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, stream ? (cudaStream_t) stream : ctx->stream);
+}
+
+int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist,
+                            uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!dev_keys || parts == 0 || k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "merge_keys: bad argument");
+    if (nq == 0) return 0;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    TopkOut o;
+    o.dist = dev_out_dist;
+    o.id = dev_out_id;
+    o.keys = dev_out_keys;
+    return launch_merge(ctx, dev_keys, parts, nq, 0, nq, k, o, 0, stream ? (cudaStream_t) stream : ctx->stream);
+}
+
+uint64_t gpann_pack_key(float dist, uint32_t id) { return pack_key(dist, id); }
+void gpann_unpack_key(uint64_t key, float* dist, uint32_t* id) {
+    if (dist) *dist = key_dist(key);
+    if (id) *id = key_id(key);
+}
+
+int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int metric,
+                        int32_t* out_assign, float* out_mindist) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !centroids || !out_assign) return fail(ctx, GPANN_E_ARG, "kmeans_assign: null argument");
+    if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");  // src/kmeans.cpp:229-231
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = pts->n, d = pts->d;
+    GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
+    if (out_mindist) GP_TRY(reserve(ctx, ctx->dist_out, std::max<size_t>(n, 1) * 4));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
+    if (n) {
+        GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p,
+                                    out_mindist ? (float*) ctx->dist_out.p : nullptr, st));
+        CU_TRY(ctx, cudaMemcpyAsync(out_assign, ctx->assign.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (out_mindist) CU_TRY(ctx, cudaMemcpyAsync(out_mindist, ctx->dist_out.p, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gpann_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc, int metric,
+                                int32_t* dev_out_assign, float* dev_out_sums, uint64_t* dev_out_counts, void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !dev_centroids || !dev_out_sums || !dev_out_counts) return fail(ctx, GPANN_E_ARG, "kmeans_partial: null argument");
+    if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
+    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+    int32_t* d_assign = dev_out_assign;
+    if (!d_assign) {
+        GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(pts->n, 1) * 4));
+        d_assign = (int32_t*) ctx->assign.p;
+    }
+    if (pts->n == 0) {
+        CU_TRY(ctx, cudaMemsetAsync(dev_out_sums, 0, kc * pts->d * 4, st));
+        CU_TRY(ctx, cudaMemsetAsync(dev_out_counts, 0, kc * 8, st));
+        return 0;
+    }
+    GP_TRY(kmeans_assign_device(ctx, pts, dev_centroids, kc, metric, d_assign, nullptr, st));
+    return cluster_sums_device(ctx, pts, d_assign, kc, 0, dev_out_sums, dev_out_counts, st);
+}
+
+int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int metric, int32_t* out_assign,
+                      uint64_t* out_sizes) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !centroids_inout || !out_sizes) return fail(ctx, GPANN_E_ARG, "kmeans_step: null argument");
+    if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
+    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = pts->n, d = pts->d;
+    GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->sums, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->counts, kc * 8));
+    GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids_inout, kc * d * 4, cudaMemcpyHostToDevice, st));
+    if (n) {
+        GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p, nullptr, st));
+        GP_TRY(cluster_sums_device(ctx, pts, (const int32_t*) ctx->assign.p, kc, 1, (float*) ctx->sums.p, (uint64_t*) ctx->counts.p, st));
+    } else {
+        CU_TRY(ctx, cudaMemsetAsync(ctx->sums.p, 0, kc * d * 4, st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->counts.p, 0, kc * 8, st));
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(centroids_inout, ctx->sums.p, kc * d * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(out_sizes, ctx->counts.p, kc * 8, cudaMemcpyDeviceToHost, st));
+    if (out_assign && n) CU_TRY(ctx, cudaMemcpyAsync(out_assign, ctx->assign.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric,
+                    double* out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !centroids || !assign || !out) return fail(ctx, GPANN_E_ARG, "objective: null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = pts->n, d = pts->d;
+    if (n == 0) {
+        *out = 0.0;
+        return 0;
+    }
+    GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->assign, n * 4));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->assign.p, assign, n * 4, cudaMemcpyHostToDevice, st));
+    ObjectiveParams p;
+    p.pts = rows_view(pts);
+    p.centroids = (const float*) ctx->cent.p;
+    p.assign = (const int32_t*) ctx->assign.p;
+    p.kc = (int) kc;
+    p.metric = metric;
+    const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
+    const int row_bytes = (int) d * elem;
+    p.spitch = odd16_pitch(row_bytes);
+    p.vec_ok = ((uintptr_t) pts->rows % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
+    const size_t smem = (size_t) kStreamTile * p.spitch;
+    if (smem > 200 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "objective: d too large");
+    const size_t ntiles = (n + kStreamTile - 1) / kStreamTile;
+    const unsigned grid = (unsigned) std::min<size_t>(ntiles, (size_t) ctx->num_sms * 4);
+    GP_TRY(reserve(ctx, ctx->misc, (size_t) grid * 8 + 64));
+    p.block_sums = (double*) ctx->misc.p;
+    double* d_out = p.block_sums + grid;
+    if (pts->storage == GPANN_STORAGE_F32) objective_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
+    else if (pts->storage == GPANN_STORAGE_U8) objective_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
+    else objective_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
+    GP_TRY(check_launch(ctx, "objective_kernel"));
+    objective_final_kernel<<<1, 32, 0, st>>>(p.block_sums, (int) grid, d_out);
+    GP_TRY(check_launch(ctx, "objective_final_kernel"));
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

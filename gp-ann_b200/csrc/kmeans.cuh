@@ -1,0 +1,266 @@
+// kmeans.cuh -- k-means form of the hot path, exact (reference arithmetic order) CUDA-core kernels.
+//
+//   kmeans_assign_kernel   NearestCenters / Top1Neighbor      (reference src/kmeans.cpp:12-27)
+//   cluster_reduce_*       SumPointsInClustersL2 / Aggregate*  (src/kmeans.cpp:116-204), deterministic order
+//   objective_kernel       ObjectiveValue                      (src/kmeans.cpp:246-249)
+//
+// The reference sums points per cluster sequentially in point order (and, for n > 19.66M at kc=1024,d=96,
+// in racy CAS-float block merges, src/kmeans.cpp:179-191, i.e. nondeterministically).  Here the members of a
+// cluster are brought together by a STABLE radix sort of (assignment, point index) pairs, cut into segments
+// of kSegRows rows, summed by one CTA per segment in a fixed order, and the segment sums are added per
+// cluster in segment order -- bitwise reproducible run to run and independent of the grid.
+#pragma once
+#include "common.cuh"
+#include "stream.cuh"
+
+namespace gpann {
+
+struct RowsView {
+    const char* rows;
+    size_t pitch;
+    int storage;
+    int d;
+    size_t n;
+    const uint32_t* ids;  // optional (norm-sorted layouts): original row index = ids[row] - id_base
+    uint32_t id_base;
+};
+
+template <int STORAGE>
+__device__ __forceinline__ void stage_rows(const RowsView& v, size_t r0, int rows_here, unsigned char* s_rows, int spitch,
+                                           int vec_ok, int tid, int nthreads) {
+    const int elem = STORAGE == kF32 ? 4 : 1;
+    const int row_bytes = v.d * elem;
+    const char* src = v.rows + r0 * v.pitch;
+    if (vec_ok) {
+        const int cpr = row_bytes >> 4;
+        for (int idx = tid; idx < rows_here * cpr; idx += nthreads) {
+            const int r = idx / cpr, c = idx - r * cpr;
+            const int4 val = __ldg(reinterpret_cast<const int4*>(src + (size_t) r * v.pitch) + c);
+            *reinterpret_cast<int4*>(s_rows + (size_t) r * spitch + c * 16) = val;
+        }
+    } else {
+        for (int idx = tid; idx < rows_here * row_bytes; idx += nthreads) {
+            const int r = idx / row_bytes, c = idx - r * row_bytes;
+            s_rows[(size_t) r * spitch + c] = (unsigned char) src[(size_t) r * v.pitch + c];
+        }
+    }
+}
+
+struct AssignParams {
+    RowsView pts;
+    const float* centroids;  // [kc, d]
+    int kc, metric;
+    int cchunk;              // centroids staged per shared-memory chunk
+    int spitch, qpitch, vec_ok;
+    int32_t* out_assign;     // [n] indexed by original row
+    float* out_mindist;      // optional [n]
+};
+
+// One thread per point, centroids streamed through shared memory in chunks; strict '<' keeps the lowest
+// centroid index on ties, -1 if nothing is below FLT_MAX (src/kmeans.cpp:12-23).
+template <int STORAGE>
+__global__ void __launch_bounds__(kStreamTile) kmeans_assign_kernel(const AssignParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    unsigned char* s_rows = smem_raw;
+    float* s_c = reinterpret_cast<float*>(s_rows + (size_t) kStreamTile * p.spitch);  // cchunk * qpitch
+    const size_t ntiles = (p.pts.n + kStreamTile - 1) / kStreamTile;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t r0 = tile * kStreamTile;
+        const int rows_here = (int) min((size_t) kStreamTile, p.pts.n - r0);
+        __syncthreads();
+        stage_rows<STORAGE>(p.pts, r0, rows_here, s_rows, p.spitch, p.vec_ok, tid, kStreamTile);
+        int best = -1;
+        float best_dist = 3.402823466e+38f;
+        const char* myrow = reinterpret_cast<const char*>(s_rows) + (size_t) tid * p.spitch;
+        for (int c0 = 0; c0 < p.kc; c0 += p.cchunk) {
+            const int nc = min(p.cchunk, p.kc - c0);
+            __syncthreads();
+            for (int i = tid; i < nc * p.pts.d; i += kStreamTile) {
+                const int c = i / p.pts.d, j = i - c * p.pts.d;
+                s_c[c * p.qpitch + j] = p.centroids[(size_t) (c0 + c) * p.pts.d + j];
+            }
+            __syncthreads();
+            if (tid < rows_here) {
+                for (int c = 0; c < nc; ++c) {
+                    const float dist = ref_distance<STORAGE>(myrow, s_c + c * p.qpitch, p.pts.d, p.metric);
+                    if (dist < best_dist) {
+                        best_dist = dist;
+                        best = c0 + c;
+                    }
+                }
+            }
+        }
+        if (tid < rows_here) {
+            const size_t row = r0 + tid;
+            const size_t orig = p.pts.ids ? (size_t) (p.pts.ids[row] - p.pts.id_base) : row;
+            if (!p.pts.ids || p.pts.ids[row] != kInvalidId) {
+                p.out_assign[orig] = best;
+                if (p.out_mindist) p.out_mindist[orig] = best_dist;
+            }
+        }
+    }
+}
+
+// ---- deterministic per-cluster sums --------------------------------------------------------------------
+constexpr int kSegRows = 1024;  // rows per reduction segment
+
+// counts[c] = number of members; seg_begin[c] = first segment index of cluster c (exclusive scan of
+// ceil(count/kSegRows)); seg_begin[kc] = total.  Single CTA, kc <= a few thousand.
+__global__ void cluster_segments_kernel(const uint64_t* counts, int kc, uint32_t* seg_begin, uint64_t* member_begin) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t s = 0;
+        uint64_t m = 0;
+        for (int c = 0; c < kc; ++c) {
+            seg_begin[c] = s;
+            member_begin[c] = m;
+            s += (uint32_t) ((counts[c] + kSegRows - 1) / kSegRows);
+            m += counts[c];
+        }
+        seg_begin[kc] = s;
+        member_begin[kc] = m;
+    }
+}
+
+// counts[c]++ for every point; also emits the radix-sort input: key = cluster (kc for unassigned -1), value = row.
+__global__ void histogram_keys_kernel(const int32_t* assign, size_t n, int kc, unsigned long long* counts, uint32_t* keys,
+                                      uint32_t* index) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int c = assign[i];
+        const bool ok = c >= 0 && c < kc;
+        if (ok) atomicAdd(&counts[c], 1ull);
+        keys[i] = ok ? (uint32_t) c : (uint32_t) kc;
+        index[i] = (uint32_t) i;
+    }
+}
+
+struct ReduceParams {
+    RowsView pts;               // rows addressed by ORIGINAL index when ids == nullptr
+    const uint32_t* members;    // point rows sorted (stably) by cluster
+    const uint32_t* seg_begin;  // [kc+1]
+    const uint64_t* member_begin;  // [kc+1]
+    int kc;
+    float* seg_sums;            // [total_segments, d]
+};
+
+// One CTA per segment: thread t owns dimension j = t % dpad and row slot t / dpad; slots are added in order.
+template <int STORAGE>
+__global__ void __launch_bounds__(256) cluster_reduce_segments_kernel(const ReduceParams p) {
+    __shared__ float s_part[256];
+    const uint32_t seg = blockIdx.x;
+    if (seg >= p.seg_begin[p.kc]) return;
+    // binary search the cluster owning this segment
+    int lo = 0, hi = p.kc;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.seg_begin[mid] <= seg) lo = mid; else hi = mid;
+    }
+    const int c = lo;
+    const uint64_t cb = p.member_begin[c], ce = p.member_begin[c + 1];
+    const uint64_t sb = cb + (uint64_t) (seg - p.seg_begin[c]) * kSegRows;
+    const uint64_t se = min(ce, sb + kSegRows);
+    const int d = p.pts.d;
+    const int dchunk = min(256, ((d + 31) / 32) * 32);
+    const int nslots = 256 / dchunk;
+    const int j_in = threadIdx.x % dchunk, slot = threadIdx.x / dchunk;
+    for (int j0 = 0; j0 < d; j0 += dchunk) {
+        const int j = j0 + j_in;
+        float acc = 0.f;
+        if (j < d && slot < nslots) {
+            for (uint64_t m = sb + slot; m < se; m += nslots) {
+                const char* row = p.pts.rows + (size_t) p.members[m] * p.pts.pitch;
+                acc += load1<STORAGE>(row, j);
+            }
+        }
+        s_part[threadIdx.x] = acc;
+        __syncthreads();
+        if (slot == 0 && j < d) {
+            float tot = s_part[j_in];
+            for (int s = 1; s < nslots; ++s) tot += s_part[s * dchunk + j_in];
+            p.seg_sums[(size_t) seg * d + j] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// Per cluster: add its segment sums in segment order; optionally divide by the member count
+// (NormalizeCentroidsL2, src/kmeans.cpp:104-114).  Empty clusters give all-zero rows.
+__global__ void cluster_finalize_kernel(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc,
+                                        int d, int normalize, float* out /*[kc,d]*/) {
+    const int c = blockIdx.x;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        float tot = 0.f;
+        for (uint32_t s = seg_begin[c]; s < seg_begin[c + 1]; ++s) tot += seg_sums[(size_t) s * d + j];
+        if (normalize && counts[c] != 0) tot = tot / (float) counts[c];
+        out[(size_t) c * d + j] = tot;
+    }
+}
+
+// Divide summed coordinates by counts (after a cross-GPU all-reduce of sums and counts).
+__global__ void normalize_centroids_kernel(float* sums, const uint64_t* counts, int kc, int d) {
+    const int c = blockIdx.x;
+    if (counts[c] == 0) return;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) sums[(size_t) c * d + j] = sums[(size_t) c * d + j] / (float) counts[c];
+}
+
+struct ObjectiveParams {
+    RowsView pts;
+    const float* centroids;
+    const int32_t* assign;  // by original row
+    int kc, metric, spitch, vec_ok;
+    double* block_sums;     // [gridDim.x]
+};
+
+// sum_i pos_distance(P_i, C_{a_i}) with every f32 term widened to double (src/kmeans.cpp:246-249); fixed-order
+// two-level reduction (per-CTA partials, summed in CTA order by objective_final_kernel).
+template <int STORAGE>
+__global__ void __launch_bounds__(kStreamTile) objective_kernel(const ObjectiveParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_red[kStreamTile];
+    const int tid = threadIdx.x;
+    unsigned char* s_rows = smem_raw;
+    double acc = 0.0;
+    const size_t ntiles = (p.pts.n + kStreamTile - 1) / kStreamTile;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t r0 = tile * kStreamTile;
+        const int rows_here = (int) min((size_t) kStreamTile, p.pts.n - r0);
+        __syncthreads();
+        stage_rows<STORAGE>(p.pts, r0, rows_here, s_rows, p.spitch, p.vec_ok, tid, kStreamTile);
+        __syncthreads();
+        if (tid < rows_here) {
+            const size_t row = r0 + tid;
+            const bool valid = !p.pts.ids || p.pts.ids[row] != kInvalidId;
+            if (valid) {
+                const size_t orig = p.pts.ids ? (size_t) (p.pts.ids[row] - p.pts.id_base) : row;
+                const int c = p.assign[orig];
+                const char* myrow = reinterpret_cast<const char*>(s_rows) + (size_t) tid * p.spitch;
+                const float* cen = p.centroids + (size_t) c * p.pts.d;
+                float dist;
+                if (p.metric == kL2) {
+                    dist = sqr_l2_ref_order([&](int i) { return load1<STORAGE>(myrow, i); }, cen, p.pts.d);
+                } else {
+                    const float ip = inner_product_ref_order([&](int i) { return load1<STORAGE>(myrow, i); }, cen, p.pts.d);
+                    dist = __fadd_rn(__fsub_rn(1.0f, ip), 1.0f);  // pos_distance under MIPS (src/dist.cpp:83-88)
+                }
+                acc += (double) dist;
+            }
+        }
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int s = kStreamTile / 2; s > 0; s >>= 1) {
+        if (tid < s) s_red[tid] += s_red[tid + s];
+        __syncthreads();
+    }
+    if (tid == 0) p.block_sums[blockIdx.x] = s_red[0];
+}
+
+__global__ void objective_final_kernel(const double* block_sums, int nblocks, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nblocks; ++i) t += block_sums[i];
+        *out = t;
+    }
+}
+
+}  // namespace gpann

@@ -1,0 +1,104 @@
+// prep.cuh -- one-time data preparation kernels: storage detection/narrowing (the reference's reader widens
+// .u8bin/.i8bin to float, src/points_io.cpp:63-111; this undoes it on upload), norms, and the norm-sorted,
+// 128-byte-row layout the tensor kernel streams (see topk_tc.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace gpann {
+
+// flags[0] &= all values are integers in [0,255]; flags[1] &= all values are integers in [-128,127]
+__global__ void detect_bytes_kernel(const float* x, size_t count, int* flags) {
+    bool u8 = true, s8 = true;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const bool integral = (v == rintf(v));
+        u8 &= integral && v >= 0.f && v <= 255.f;
+        s8 &= integral && v >= -128.f && v <= 127.f;
+    }
+    if (!__all_sync(0xffffffffu, u8) && (threadIdx.x & 31) == 0) atomicAnd(&flags[0], 0);
+    if (!__all_sync(0xffffffffu, s8) && (threadIdx.x & 31) == 0) atomicAnd(&flags[1], 0);
+}
+
+// float rows [n,d] -> byte rows [n, pitch] (zero padded), as u8 or s8 bit patterns
+__global__ void narrow_rows_kernel(const float* x, size_t n, int d, int pitch, unsigned char* out) {
+    const size_t total = n * (size_t) pitch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t r = i / pitch;
+        const int j = (int) (i - r * pitch);
+        out[i] = j < d ? (unsigned char) (int) x[r * d + j] : 0;
+    }
+}
+
+// Per-row squared norm of byte rows (exact int32; d <= 256 keeps it below 2^24).
+__global__ void byte_norms_kernel(const unsigned char* rows, size_t n, int d, size_t pitch, int is_signed, uint32_t* norms,
+                                  uint32_t* index) {
+    for (size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (size_t) gridDim.x * blockDim.x) {
+        const unsigned char* row = rows + r * pitch;
+        int acc = 0;
+        for (int j = 0; j < d; ++j) {
+            const int v = is_signed ? (int) (int8_t) row[j] : (int) row[j];
+            acc += v * v;
+        }
+        norms[r] = (uint32_t) acc;
+        if (index) index[r] = (uint32_t) r;
+    }
+}
+
+// Gather rows into norm order, padded to 128-byte rows; rows >= n are zero padding with id = kInvalidId.
+// One warp per output row (32 lanes x 4 bytes).
+__global__ void gather_sorted_rows_kernel(const unsigned char* rows, size_t n, int d, size_t pitch, const uint32_t* perm,
+                                          const uint32_t* sorted_norms, uint32_t id_base, size_t n_pad,
+                                          unsigned char* out_rows /*[n_pad,128]*/, int32_t* out_norms, uint32_t* out_ids) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    for (size_t r = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_pad; r += warps) {
+        uint32_t word = 0;
+        if (r < n) {
+            const unsigned char* src = rows + (size_t) perm[r] * pitch;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = lane * 4 + b;
+                if (j < d) word |= (uint32_t) src[j] << (8 * b);
+            }
+        }
+        reinterpret_cast<uint32_t*>(out_rows + r * 128)[lane] = word;
+        if (lane == 0) {
+            out_norms[r] = r < n ? (int32_t) sorted_norms[r] : 0x3fffffff;
+            out_ids[r] = r < n ? id_base + perm[r] : kInvalidId;
+        }
+    }
+}
+
+// Queries for the byte tensor kernel: float [nq,d] -> byte rows [nq_pad,128] + int32 norms; clears *ok when a
+// coordinate is not an integer in the storage's range (the caller then takes the exact float path instead).
+__global__ void prep_queries_bytes_kernel(const float* q, int nq, int d, int nq_pad, int is_signed, unsigned char* out_rows,
+                                          int32_t* out_norms, int* ok) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nq_pad; r += warps) {
+        uint32_t word = 0;
+        int nrm = 0;
+        bool good = true;
+        if (r < nq) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = lane * 4 + b;
+                if (j < d) {
+                    const float v = q[(size_t) r * d + j];
+                    const float lo = is_signed ? -128.f : 0.f, hi = is_signed ? 127.f : 255.f;
+                    good &= (v == rintf(v)) && v >= lo && v <= hi;
+                    const int iv = (int) v;
+                    nrm += iv * iv;
+                    word |= (uint32_t) (iv & 0xFF) << (8 * b);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        reinterpret_cast<uint32_t*>(out_rows + (size_t) r * 128)[lane] = word;
+        if (lane == 0) out_norms[r] = nrm;
+        if (!__all_sync(0xffffffffu, good) && lane == 0) atomicAnd(ok, 0);
+    }
+}
+
+}  // namespace gpann

@@ -1,0 +1,239 @@
+// stream.cuh -- HBM-streaming exact scan (CUDA cores) + key merge.
+//
+// Replaces the reference's scalar triple loop `for query: for point: distance(); TopN.Add()`
+// (src/recall.h:27-37, src/defs.cpp:87-96, src/inverted_index.h:43-75) for SMALL query batches, where the path
+// is bound by streaming the point rows from HBM, and serves as the exact (reference summation order) kernel
+// for every shape the tensor kernel does not cover.
+//
+// Work decomposition: a CTA walks point tiles of kTile rows (coalesced 16-byte loads into padded shared
+// memory), one thread per point.  For each query of the current batch the thread computes the distance in
+// the reference's own arithmetic order and, if the (distance,id) key beats the CTA's current k-th best for
+// that query, appends it to a shared-memory candidate buffer; a warp compacts a buffer (register bitonic
+// select) before it could overflow, which also tightens the threshold.  Each CTA finally emits its k best
+// keys per query and merge_keys_kernel reduces over CTAs.
+#pragma once
+#include "common.cuh"
+
+namespace gpann {
+
+constexpr int kStreamTile = 128;  // points per tile == threads per CTA
+
+struct StreamParams {
+    const char* rows;       // first row of the point set
+    size_t pitch;           // bytes between rows
+    int storage;            // kF32 / kU8 / kS8
+    int d;
+    size_t row_begin, row_end;  // scanned row range
+    const uint32_t* ids;    // optional per-row ids (norm-sorted layouts); else id = id_base + row
+    uint32_t id_base;
+    uint32_t id_lo, id_hi;  // keep only ids in [id_lo, id_hi)
+    const float* queries;   // [nq, d]
+    int nq, k, metric;
+    int qb;                 // queries per batch (blockIdx.y selects the batch)
+    int cap;                // candidate buffer capacity per query (power of two, >= k + kStreamTile)
+    int spitch;             // shared-memory row pitch in bytes (odd multiple of 16)
+    int qpitch;             // shared-memory query pitch in floats (multiple of 4)
+    int vec_ok;             // rows can be fetched with 16-byte loads
+    uint64_t* partial;      // [gridDim.x, nq, k]
+};
+
+template <int STORAGE>
+__device__ __forceinline__ void load8(const char* row, int i, float (&x)[8]) {
+    if constexpr (STORAGE == kF32) {
+        const float4 a = *reinterpret_cast<const float4*>(row + (size_t) i * 4);
+        const float4 b = *reinterpret_cast<const float4*>(row + (size_t) i * 4 + 16);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(row + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t word = j < 4 ? w.x : w.y;
+            const uint32_t byte = (word >> (8 * (j & 3))) & 0xFFu;
+            x[j] = STORAGE == kU8 ? (float) byte : (float) (int) (int8_t) byte;
+        }
+    }
+}
+template <int STORAGE>
+__device__ __forceinline__ float load1(const char* row, int i) {
+    if constexpr (STORAGE == kF32) return reinterpret_cast<const float*>(row)[i];
+    if constexpr (STORAGE == kU8) return (float) reinterpret_cast<const uint8_t*>(row)[i];
+    return (float) reinterpret_cast<const int8_t*>(row)[i];
+}
+
+// Distance of one shared-memory point row to one shared-memory query row, reference arithmetic order.
+template <int STORAGE>
+__device__ __forceinline__ float ref_distance(const char* row, const float* q, int d, int metric) {
+    if (metric == kL2) {
+        float l[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int d16 = d & ~15;
+        for (int i = 0; i < d16; i += 8) {
+            float x[8];
+            load8<STORAGE>(row, i, x);
+            const float4 qa = *reinterpret_cast<const float4*>(q + i);
+            const float4 qb = *reinterpret_cast<const float4*>(q + i + 4);
+            float t;
+            t = x[0] - qa.x; l[0] = __fmaf_rn(t, t, l[0]);
+            t = x[1] - qa.y; l[1] = __fmaf_rn(t, t, l[1]);
+            t = x[2] - qa.z; l[2] = __fmaf_rn(t, t, l[2]);
+            t = x[3] - qa.w; l[3] = __fmaf_rn(t, t, l[3]);
+            t = x[4] - qb.x; l[4] = __fmaf_rn(t, t, l[4]);
+            t = x[5] - qb.y; l[5] = __fmaf_rn(t, t, l[5]);
+            t = x[6] - qb.z; l[6] = __fmaf_rn(t, t, l[6]);
+            t = x[7] - qb.w; l[7] = __fmaf_rn(t, t, l[7]);
+        }
+        float res = __fadd_rn(l[0], l[1]);
+#pragma unroll
+        for (int j = 2; j < 8; ++j) res = __fadd_rn(res, l[j]);
+        float tail = 0.f;
+        for (int i = d16; i < d; ++i) {
+            const float t = load1<STORAGE>(row, i) - q[i];
+            tail = __fmaf_rn(t, t, tail);
+        }
+        return __fadd_rn(res, tail);
+    } else {
+        float r = 0.f;
+        for (int i = 0; i < d; ++i) r = __fmaf_rn(q[i], load1<STORAGE>(row, i), r);
+        return __fsub_rn(1.0f, r);
+    }
+}
+
+template <int STORAGE>
+__global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q0 = blockIdx.y * p.qb;
+    const int nqb = min(p.qb, p.nq - q0);
+    const int elem = STORAGE == kF32 ? 4 : 1;
+    const int row_bytes = p.d * elem;
+
+    unsigned char* s_rows = smem_raw;                                            // kStreamTile * spitch
+    float* s_q = reinterpret_cast<float*>(s_rows + (size_t) kStreamTile * p.spitch);  // qb * qpitch
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(s_q + (size_t) p.qb * p.qpitch);    // qb * cap
+    uint64_t* s_thr = s_buf + (size_t) p.qb * p.cap;                              // qb
+    int* s_cnt = reinterpret_cast<int*>(s_thr + p.qb);                            // qb
+
+    for (int i = tid; i < nqb * p.d; i += kStreamTile) {
+        const int q = i / p.d, j = i - q * p.d;
+        s_q[q * p.qpitch + j] = p.queries[(size_t) (q0 + q) * p.d + j];
+    }
+    for (int q = tid; q < nqb; q += kStreamTile) {
+        s_thr[q] = kEmptyKey;
+        s_cnt[q] = 0;
+    }
+    __syncthreads();
+
+    const size_t nrows = p.row_end - p.row_begin;
+    const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t r0 = p.row_begin + tile * kStreamTile;
+        const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
+        const char* src = p.rows + r0 * p.pitch;
+        if (p.vec_ok) {
+            const int cpr = row_bytes >> 4;  // 16-byte chunks per row (row_bytes % 16 == 0 when vec_ok)
+            for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
+                const int r = idx / cpr, c = idx - r * cpr;
+                const int4 v = __ldg(reinterpret_cast<const int4*>(src + (size_t) r * p.pitch) + c);
+                *reinterpret_cast<int4*>(s_rows + (size_t) r * p.spitch + c * 16) = v;
+            }
+        } else {
+            for (int idx = tid; idx < rows_here * row_bytes; idx += kStreamTile) {
+                const int r = idx / row_bytes, c = idx - r * row_bytes;
+                s_rows[(size_t) r * p.spitch + c] = (unsigned char) src[(size_t) r * p.pitch + c];
+            }
+        }
+        __syncthreads();
+        if (tid < rows_here) {
+            const size_t row = r0 + tid;
+            const uint32_t id = p.ids ? p.ids[row] : p.id_base + (uint32_t) row;
+            if (id != kInvalidId && id >= p.id_lo && id < p.id_hi) {
+                const char* myrow = reinterpret_cast<const char*>(s_rows) + (size_t) tid * p.spitch;
+                for (int q = 0; q < nqb; ++q) {
+                    const float dist = ref_distance<STORAGE>(myrow, s_q + q * p.qpitch, p.d, p.metric);
+                    const uint64_t key = pack_key(dist, id);
+                    if (key < s_thr[q]) {
+                        const int pos = atomicAdd(&s_cnt[q], 1);
+                        s_buf[(size_t) q * p.cap + pos] = key;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // compact any buffer that could overflow during the next tile
+        for (int q = warp; q < nqb; q += kStreamTile / 32) {
+            const int cnt = s_cnt[q];
+            if (cnt > p.cap - kStreamTile) {
+                uint64_t* b = s_buf + (size_t) q * p.cap;
+                const uint64_t kth = warp_select_topk_dyn(b, cnt, p.k, b, lane, p.cap);
+                if (lane == 0) {
+                    s_cnt[q] = min(cnt, p.k);
+                    s_thr[q] = kth;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // final selection -> this CTA's partial result
+    for (int q = warp; q < nqb; q += kStreamTile / 32) {
+        uint64_t* b = s_buf + (size_t) q * p.cap;
+        uint64_t* dst = p.partial + ((size_t) blockIdx.x * p.nq + (q0 + q)) * p.k;
+        warp_select_topk_dyn(b, s_cnt[q], p.k, dst, lane, p.cap);
+    }
+}
+
+// Merge `parts` ascending key lists per query into the k smallest.  One warp per query; keys [parts, nq, k].
+// Output: any of out_dist [nq,k] (float), out_id [nq,k], out_keys [nq,k], out_count [nq], out_kth [nq] (the
+// reference's Top().first: the largest kept distance).
+struct MergeParams {
+    const uint64_t* keys;
+    size_t parts, nq;
+    size_t nq_stride;  // queries per part in `keys` (>= nq: padded layouts)
+    int k;
+    int cap;  // power of two >= 2*k' where k' = 32-rounded k; selection window
+    float* out_dist;
+    uint32_t* out_id;
+    uint64_t* out_keys;
+    uint32_t* out_count;
+    float* out_kth;
+};
+
+__global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t q = (size_t) blockIdx.x * 4 + warp;
+    if (q >= p.nq) return;
+    uint64_t* win = reinterpret_cast<uint64_t*>(smem_raw) + (size_t) warp * p.cap;  // [cap]
+    // running best k in win[0..k), incoming keys appended behind, select when the window is full
+    int cnt = 0;
+    const int chunk = p.cap - p.k;  // free slots after keeping k
+    const size_t total = p.parts * (size_t) p.k;
+    for (size_t base = 0; base < total; base += chunk) {
+        const int take = (int) min((size_t) chunk, total - base);
+        for (int i = lane; i < take; i += 32) {
+            const size_t g = base + i;
+            const size_t part = g / p.k, r = g - part * p.k;
+            win[cnt + i] = p.keys[(part * p.nq_stride + q) * p.k + r];
+        }
+        __syncwarp();
+        cnt += take;
+        warp_select_topk_dyn(win, cnt, p.k, win, lane, p.cap);
+        cnt = min(cnt, p.k);
+    }
+    __syncwarp();
+    uint32_t valid = 0;
+    for (int i = lane; i < p.k; i += 32) {
+        const uint64_t key = win[i];
+        const bool ok = key != kEmptyKey;
+        valid += ok;
+        if (p.out_keys) p.out_keys[q * p.k + i] = key;
+        if (p.out_dist) p.out_dist[q * p.k + i] = ok ? key_dist(key) : __int_as_float(0x7f800000);
+        if (p.out_id) p.out_id[q * p.k + i] = ok ? key_id(key) : kInvalidId;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    if (lane == 0) {
+        if (p.out_count) p.out_count[q] = valid;
+        if (p.out_kth) p.out_kth[q] = valid ? key_dist(win[valid - 1]) : __int_as_float(0x7f800000);
+    }
+}
+
+}  // namespace gpann

@@ -1,0 +1,250 @@
+"""ctypes declarations for every symbol of include/gpann.h, and thin RAII wrappers (Context, Points)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+L2, MIPS = 0, 1
+STORAGE_AUTO, STORAGE_F32, STORAGE_U8, STORAGE_S8 = 0, 1, 2, 3
+ALGO_AUTO, ALGO_STREAM, ALGO_TENSOR = 0, 1, 2
+INVALID_ID = 0xFFFFFFFF
+EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
+
+# every exported symbol of include/gpann.h: name -> (restype, argtypes)
+_vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
+SYMBOLS = {
+    "gpann_init": (_i, [C.POINTER(_vp), _i]),
+    "gpann_destroy": (None, [_vp]),
+    "gpann_last_error": (C.c_char_p, [_vp]),
+    "gpann_device": (_i, [_vp]),
+    "gpann_set_algo": (_i, [_vp, _i]),
+    "gpann_launch_count": (_u64, [_vp]),
+    "gpann_last_algo": (C.c_char_p, [_vp]),
+    "gpann_points_upload": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
+    "gpann_points_upload_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
+    "gpann_points_from_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, C.POINTER(_vp)]),
+    "gpann_points_free": (None, [_vp]),
+    "gpann_points_n": (_sz, [_vp]),
+    "gpann_points_d": (_sz, [_vp]),
+    "gpann_points_storage": (_i, [_vp]),
+    "gpann_topk": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "gpann_kth_distance": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "gpann_topk_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "gpann_topk_range": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "gpann_merge_keys_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
+    "gpann_pack_key": (_u64, [C.c_float, _u32]),
+    "gpann_unpack_key": (None, [_u64, C.POINTER(C.c_float), C.POINTER(_u32)]),
+    "gpann_kmeans_assign": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "gpann_kmeans_step": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
+    "gpann_kmeans_partial_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
+    "gpann_objective": (_i, [_vp, _vp, _vp, _sz, _vp, _i, C.POINTER(C.c_double)]),
+}
+
+
+class GpannError(RuntimeError):
+    """Raised for every non-zero return of the C ABI (the reference throws std::runtime_error, kmeans.cpp:229)."""
+
+
+def lib_path():
+    return os.environ.get("GPANN_LIB", os.path.join(os.path.dirname(HERE), "libgpann_cuda.so"))
+
+
+_lib = None
+
+
+def load_library():
+    """Load libgpann_cuda.so and declare all prototypes.  Loading needs no GPU; gpann_init does."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise GpannError(f"{path} is missing: build it with `python gp-ann_b200/build.py` (there is no CPU fallback)")
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def pack_key(dist, idx):
+    return int(load_library().gpann_pack_key(float(dist), int(idx)))
+
+
+def unpack_keys(keys):
+    """Vectorised inverse of the key packing: uint64 array -> (float32 distances, uint32 ids)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    o = (keys >> np.uint64(32)).astype(np.uint32)
+    neg = (o & np.uint32(0x80000000)) == 0
+    bits = np.where(neg, ~o, o & np.uint32(0x7FFFFFFF)).astype(np.uint32)
+    return bits.view(np.float32), (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One gpann_ctx (one CUDA device).  Externally synchronised: one call at a time."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.gpann_init(C.byref(h), int(device))
+        if rc != 0:
+            raise GpannError(f"gpann_init(device={device}) failed with code {rc}: no usable sm_100 CUDA device "
+                             "(there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpann_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        if rc != 0:
+            raise GpannError(f"gpann error {rc}: {self.lib.gpann_last_error(self.h).decode()}")
+
+    def set_algo(self, algo):
+        self.check(self.lib.gpann_set_algo(self.h, algo))
+
+    @property
+    def last_algo(self):
+        return self.lib.gpann_last_algo(self.h).decode()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gpann_launch_count(self.h))
+
+    # ---- point sets ----
+    def upload(self, rows, storage=STORAGE_AUTO, id_base=0):
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype in (np.uint8, np.int8):
+            return self.upload_bytes(rows, id_base)
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        n, d = rows.shape
+        h = C.c_void_p()
+        self.check(self.lib.gpann_points_upload(self.h, _ptr(rows), n, d, storage, id_base, C.byref(h)))
+        return Points(self, h)
+
+    def upload_bytes(self, rows, id_base=0):
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype in (np.uint8, np.int8)
+        n, d = rows.shape
+        h = C.c_void_p()
+        self.check(self.lib.gpann_points_upload_bytes(self.h, _ptr(rows), n, d, int(rows.dtype == np.int8), id_base,
+                                                      C.byref(h)))
+        return Points(self, h)
+
+    def from_device(self, dev_ptr, n, d, storage, id_base=0, stream=None, keepalive=None):
+        h = C.c_void_p()
+        self.check(self.lib.gpann_points_from_device(self.h, C.c_void_p(dev_ptr), n, d, storage, id_base,
+                                                     C.c_void_p(stream or 0), C.byref(h)))
+        p = Points(self, h)
+        p.keepalive = keepalive  # the rows are borrowed
+        return p
+
+    # ---- top-k ----
+    def topk(self, pts, queries, k, metric=L2, row_range=None, want_dist=True, want_count=True):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        dist = np.empty((nq, k), np.float32) if want_dist else None
+        ids = np.empty((nq, k), np.uint32)
+        cnt = np.empty(nq, np.uint32) if want_count else None
+        if row_range is None:
+            rc = self.lib.gpann_topk(self.h, pts.h, _ptr(q), nq, k, metric, _ptr(dist), _ptr(ids), _ptr(cnt))
+        else:
+            rc = self.lib.gpann_topk_range(self.h, pts.h, row_range[0], row_range[1], _ptr(q), nq, k, metric, _ptr(dist),
+                                           _ptr(ids), _ptr(cnt))
+        self.check(rc)
+        return dist, ids, cnt
+
+    def kth_distance(self, pts, queries, k, metric=L2):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty(q.shape[0], np.float32)
+        self.check(self.lib.gpann_kth_distance(self.h, pts.h, _ptr(q), q.shape[0], k, metric, _ptr(out)))
+        return out
+
+    def topk_device(self, pts, dev_queries, nq, k, dev_out_keys, metric=L2, stream=None):
+        self.check(self.lib.gpann_topk_device(self.h, pts.h, C.c_void_p(dev_queries), nq, k, metric,
+                                              C.c_void_p(dev_out_keys), C.c_void_p(stream or 0)))
+
+    def merge_keys_device(self, dev_keys, parts, nq, k, dev_out_dist=None, dev_out_id=None, dev_out_keys=None, stream=None):
+        self.check(self.lib.gpann_merge_keys_device(self.h, C.c_void_p(dev_keys), parts, nq, k,
+                                                    C.c_void_p(dev_out_dist or 0), C.c_void_p(dev_out_id or 0),
+                                                    C.c_void_p(dev_out_keys or 0), C.c_void_p(stream or 0)))
+
+    # ---- k-means ----
+    def kmeans_assign(self, pts, centroids, metric=L2, want_mindist=False):
+        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        out = np.empty(pts.n, np.int32)
+        md = np.empty(pts.n, np.float32) if want_mindist else None
+        self.check(self.lib.gpann_kmeans_assign(self.h, pts.h, _ptr(c), c.shape[0], metric, _ptr(out), _ptr(md)))
+        return (out, md) if want_mindist else out
+
+    def kmeans_step(self, pts, centroids, metric=L2):
+        """One Lloyd round.  Returns (assignment, new centroids incl. all-zero rows of empty clusters, sizes)."""
+        c = np.ascontiguousarray(centroids, dtype=np.float32).copy()
+        assign = np.empty(pts.n, np.int32)
+        sizes = np.empty(c.shape[0], np.uint64)
+        self.check(self.lib.gpann_kmeans_step(self.h, pts.h, _ptr(c), c.shape[0], metric, _ptr(assign), _ptr(sizes)))
+        return assign, c, sizes
+
+    def kmeans_partial_device(self, pts, dev_centroids, kc, dev_sums, dev_counts, dev_assign=None, metric=L2, stream=None):
+        self.check(self.lib.gpann_kmeans_partial_device(self.h, pts.h, C.c_void_p(dev_centroids), kc, metric,
+                                                        C.c_void_p(dev_assign or 0), C.c_void_p(dev_sums),
+                                                        C.c_void_p(dev_counts), C.c_void_p(stream or 0)))
+
+    def objective(self, pts, centroids, assign, metric=L2):
+        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        a = np.ascontiguousarray(assign, dtype=np.int32)
+        out = C.c_double()
+        self.check(self.lib.gpann_objective(self.h, pts.h, _ptr(c), c.shape[0], _ptr(a), metric, C.byref(out)))
+        return out.value
+
+
+class Points:
+    """A device-resident point set (gpann_points)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h, self.keepalive = ctx, h, None
+
+    @property
+    def n(self):
+        return int(self.ctx.lib.gpann_points_n(self.h))
+
+    @property
+    def d(self):
+        return int(self.ctx.lib.gpann_points_d(self.h))
+
+    @property
+    def storage(self):
+        return int(self.ctx.lib.gpann_points_storage(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gpann_points_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,127 @@
+/* gpann.h -- C ABI of libgpann_cuda.so: gp-ann's brute-force distance + top-k hot path on B200 (sm_100a).
+ *
+ * The reference (larsgottesbueren/gp-ann) has no plugin / FFI layer: the path sits behind plain C++ free
+ * functions (src/dist.h:3-15, src/topn.h:6-32, src/recall.h:10,25, src/kmeans.h:5-8, src/defs.h:50).  The
+ * drop-in C++ headers in gp-ann_b200/cxx/ keep those signatures and forward the batched ones to the entry
+ * points below; INTEGRATION.md shows the binding.  Each entry point names the reference interface it
+ * replaces (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no exceptions and no STL across the boundary.
+ *  - One gpann_ctx per CUDA device; a ctx is externally synchronised (one call at a time).
+ *  - Every function returns 0 on success or a negative GPANN_E_* code; gpann_last_error(ctx) has the text.
+ *  - Host entry points borrow caller-owned host buffers for the duration of the call; the library owns all
+ *    device memory behind the opaque handles.  The *_device entry points take device pointers and a
+ *    cudaStream_t (as void*) and are asynchronous on that stream.
+ *  - There is NO CPU fallback: without a usable CUDA device gpann_init fails with GPANN_E_CUDA.
+ *  - Results are "keys": a (distance, id) pair packed into 64 bits whose unsigned order is the reference's
+ *    std::pair<float,uint32_t> lexicographic order (src/topn.h:12-19): ties on distance keep the smaller id.
+ */
+#ifndef GPANN_H
+#define GPANN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpann_ctx gpann_ctx;
+typedef struct gpann_points gpann_points;
+
+enum { GPANN_OK = 0, GPANN_E_CUDA = -1, GPANN_E_ARG = -2, GPANN_E_OOM = -3, GPANN_E_UNSUPPORTED = -4 };
+
+/* Distance metric.  The reference selects it at compile time (-DMIPS_DISTANCE, src/dist.cpp:75-81). */
+enum { GPANN_METRIC_L2 = 0, GPANN_METRIC_MIPS = 1 };
+
+/* Point storage in HBM.  AUTO narrows float rows to U8 / S8 when every coordinate is an integer in range
+ * (BigANN .u8bin / .i8bin data is widened to float by the reference's reader, src/points_io.cpp:63-111). */
+enum { GPANN_STORAGE_AUTO = 0, GPANN_STORAGE_F32 = 1, GPANN_STORAGE_U8 = 2, GPANN_STORAGE_S8 = 3 };
+
+/* Which kernel family serves gpann_topk*: AUTO picks by shape; STREAM = CUDA-core HBM-streaming scan;
+ * TENSOR = tcgen05/TMEM tile kernel (fails with GPANN_E_UNSUPPORTED where it does not apply). */
+enum { GPANN_ALGO_AUTO = 0, GPANN_ALGO_STREAM = 1, GPANN_ALGO_TENSOR = 2 };
+
+#define GPANN_INVALID_ID 0xFFFFFFFFu
+#define GPANN_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int gpann_init(gpann_ctx** out, int device);
+void gpann_destroy(gpann_ctx* ctx);
+const char* gpann_last_error(const gpann_ctx* ctx);
+int gpann_device(const gpann_ctx* ctx);
+int gpann_set_algo(gpann_ctx* ctx, int algo);
+/* Number of kernel launches issued by this ctx since init (bench.py's gpu_launches claim). */
+uint64_t gpann_launch_count(const gpann_ctx* ctx);
+/* Name of the kernel family the last gpann_topk* call used ("stream", "tensor_u8", ...). */
+const char* gpann_last_algo(const gpann_ctx* ctx);
+
+/* ---- point sets: replaces PointSet (src/defs.h:10-21) as the scanned operand --------------------------- */
+/* Upload n rows of d floats (row-major, as PointSet::coordinates).  Ids reported by gpann_topk are
+ * id_base + row index (id_base lets a caller shard rows across devices/processes and keep global ids). */
+int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base,
+                        gpann_points** out);
+/* Byte rows as stored in .u8bin / .i8bin files (src/points_io.cpp:63-111 without the float widening). */
+int gpann_points_upload_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed,
+                              uint32_t id_base, gpann_points** out);
+/* Rows already resident in device memory: storage is F32 (float rows), U8 or S8 (byte rows). */
+int gpann_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, size_t d, int storage, uint32_t id_base,
+                             void* stream, gpann_points** out);
+void gpann_points_free(gpann_points* pts);
+size_t gpann_points_n(const gpann_points* pts);
+size_t gpann_points_d(const gpann_points* pts);
+int gpann_points_storage(const gpann_points* pts);
+
+/* ---- exact top-k: replaces ComputeGroundTruth (src/recall.h:25-39), ComputeDistanceToKthNeighbor
+ *      (src/recall.h:10-23), ClosestLeaders (src/defs.cpp:87-96) and the scans of
+ *      InvertedIndex::Query/QueryBucket (src/inverted_index.h:43-75) ------------------------------------- */
+/* queries: nq rows of d floats on the host.  out_dist/out_id are [nq,k], ascending by (distance,id);
+ * out_count[q] = min(k, n) (src/topn.h:21-29); unused slots hold +inf / GPANN_INVALID_ID.
+ * out_dist or out_count may be NULL. */
+int gpann_topk(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
+               float* out_dist, uint32_t* out_id, uint32_t* out_count);
+/* Only the kth distance (Top().first of the reference's heap): out_kth[nq]. */
+int gpann_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
+                       float* out_kth);
+/* Device-resident form: dev_queries = nq x d floats in device memory; dev_out_keys = [nq,k] uint64 keys
+ * ascending (GPANN_EMPTY_KEY padded).  Asynchronous on `stream`.  This is the per-shard step of the
+ * multi-GPU path: every rank runs it on its shard, all-gathers the keys and calls gpann_merge_keys_device. */
+int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
+                      uint64_t* dev_out_keys, void* stream);
+/* Range-restricted scan (InvertedIndex buckets, src/inverted_index.h:43-75): only rows in
+ * [row_begin,row_end) are scanned; ids are id_base + row. */
+int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries,
+                     size_t nq, int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+/* Merge `parts` key lists per query ([parts,nq,k], e.g. the all-gathered per-GPU candidates) into the k
+ * smallest keys per query; writes distances/ids (either may be NULL) and/or merged keys. */
+int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k,
+                            float* dev_out_dist, uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream);
+/* Key <-> (distance,id) on the host, for callers that exchange keys themselves. */
+uint64_t gpann_pack_key(float dist, uint32_t id);
+void gpann_unpack_key(uint64_t key, float* dist, uint32_t* id);
+
+/* ---- k-means: replaces NearestCenters / AggregateClusters* / KMeans / ObjectiveValue
+ *      (src/kmeans.cpp:12-27, 116-204, 228-244, 246-249).  L2 build only. --------------------------------- */
+/* argmin over centroids with strict '<' (lowest index wins ties); out_mindist may be NULL. */
+int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int metric,
+                        int32_t* out_assign, float* out_mindist);
+/* One Lloyd round: assign, sum points per cluster, divide by the cluster size.  centroids_inout [kc,d] is
+ * overwritten with the means (rows of empty clusters are all-zero, as in the reference before
+ * RemoveEmptyClusters, src/kmeans.cpp:29-50, which stays in the host wrapper).  out_assign may be NULL. */
+int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int metric,
+                      int32_t* out_assign, uint64_t* out_sizes);
+/* Device form used by the multi-GPU path: writes this shard's per-cluster coordinate SUMS [kc,d] (float)
+ * and counts [kc] (uint64) and the assignment [n] (int32, may be NULL); the caller all-reduces sums and
+ * counts (NCCL) and divides. */
+int gpann_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc,
+                                int metric, int32_t* dev_out_assign, float* dev_out_sums, uint64_t* dev_out_counts,
+                                void* stream);
+/* sum_i pos_distance(P_i, C_assign[i]) accumulated in double (src/kmeans.cpp:246-249). */
+int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign,
+                    int metric, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPANN_H */
