@@ -1,31 +1,56 @@
-"""Build libgpann_cuda.so (sm_100a only) in-tree with nvcc.  Cross-compiles without a GPU."""
+"""Build libgpann_cuda.so (sm_100a only) in-tree with nvcc.  Cross-compiles without a GPU.
+
+Each translation unit is compiled to an object in parallel (-gencode arch=compute_100a,code=sm_100a -lineinfo),
+then linked into gp-ann_b200/libgpann_cuda.so (static cudart, no other dependency: the driver entry point for
+tensor maps is resolved at run time).
+"""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libgpann_cuda.so")
-SOURCES = ["gpann_api.cu"]
-HEADERS = ["common.cuh", "stream.cuh", "kmeans.cuh", "prep.cuh", "topk_tc.cuh", os.path.join("..", "..", "include", "gpann.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-cudart", "static"]
+SOURCES = ["gpann_api.cu", "topk_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
+HEADERS = ["common.cuh", "distance.cuh", "params.h", os.path.join("..", "..", "include", "gpann.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr"]
 
 
-def up_to_date():
-    if not os.path.exists(OUT):
-        return False
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+def _nvcc():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src, force, verbose):
+    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if force or _stale(obj, deps):
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        return obj, True
+    return obj, False
 
 
 def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
+    objs = [o for o, _ in results]
+    if force or any(changed for _, changed in results) or not os.path.exists(OUT):
+        subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
     return OUT
 
 

@@ -134,17 +134,17 @@ __device__ __forceinline__ uint64_t warp_select_topk(const uint64_t* buf, int cn
     return kth;
 }
 
-// Runtime dispatch on the number of keys per lane.
+// Runtime dispatch on the number of keys per lane (cap <= 32*MAXE, checked by the host API).
 // __noinline__: one copy per translation unit (the unrolled sorting networks are large) and the callers' hot
 // loops keep their own register budget; every call site is a rare path.
-__device__ __noinline__ uint64_t warp_select_topk_dyn(const uint64_t* buf, int cnt, int k, uint64_t* dst, int lane,
-                                                      int cap) {
+template <int MAXE>
+__device__ __noinline__ uint64_t warp_select_topk_dyn(const uint64_t* buf, int cnt, int k, uint64_t* dst, int lane, int cap) {
     if (cap <= 32) return warp_select_topk<1>(buf, cnt, k, dst, lane);
     if (cap <= 64) return warp_select_topk<2>(buf, cnt, k, dst, lane);
-    if (cap <= 128) return warp_select_topk<4>(buf, cnt, k, dst, lane);
-    if (cap <= 256) return warp_select_topk<8>(buf, cnt, k, dst, lane);
-    if (cap <= 512) return warp_select_topk<16>(buf, cnt, k, dst, lane);
-    return warp_select_topk<32>(buf, cnt, k, dst, lane);  // cap <= 1024 (checked by the host API)
+    if (cap <= 128 || MAXE <= 4) return warp_select_topk<4>(buf, cnt, k, dst, lane);
+    if (cap <= 256 || MAXE <= 8) return warp_select_topk<8>(buf, cnt, k, dst, lane);
+    if (cap <= 512 || MAXE <= 16) return warp_select_topk<16>(buf, cnt, k, dst, lane);
+    return warp_select_topk<32>(buf, cnt, k, dst, lane);
 }
 
 __host__ __device__ __forceinline__ int pow2_ceil(int x) {

@@ -1,11 +1,12 @@
-// gpann_api.cu -- the C ABI of libgpann_cuda.so (declared in include/gpann.h) over the sm_100a kernels.
-// No CPU fallback lives here: every compute entry point launches CUDA kernels or fails.
+// gpann_api.cu -- the C ABI of libgpann_cuda.so (declared in include/gpann.h): host-side orchestration over the
+// sm_100a kernels of stream.cu / topk_tc.cu / kmeans.cu / prep.cu.  No CPU fallback lives here: every compute
+// entry point launches CUDA kernels or fails.
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -13,10 +14,7 @@
 
 #include "../../include/gpann.h"
 #include "common.cuh"
-#include "kmeans.cuh"
-#include "prep.cuh"
-#include "stream.cuh"
-#include "topk_tc.cuh"
+#include "params.h"
 
 using namespace gpann;
 
@@ -39,10 +37,14 @@ struct gpann_ctx {
     uint64_t launches = 0;
     const char* last_algo = "none";
     EncodeTiledFn encode_tiled = nullptr;
-    int tc_mode = 0;  // GPANN_TC_MODE env: 1 = roofline probe (MMA + TMEM loads only)
+    int tc_mode = 0;     // GPANN_TC_MODE env: 1 = probe (MMA + TMEM loads + max), 2 = probe (MMA issue only)
+    int tc_prepass = 1;  // GPANN_TC_PREPASS env: 0 disables the sample pre-pass (cold-start thresholds)
+    int timing = 0;
+    bool timed = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // grow-only scratch, reused across calls (a ctx is externally synchronised)
-    DevBuf partial, cand, qrows, qnorm, flags, keys_out, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b,
-        sort_c, sort_d, segsums, cent, sums, counts, assign;
+    DevBuf partial, cand, qrows, qnorm, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
+        sort_d, segsums, cent, sums, counts, assign;
 };
 
 struct gpann_points {
@@ -54,7 +56,7 @@ struct gpann_points {
     void* rows = nullptr;
     size_t pitch = 0;
     bool owns_rows = true;
-    // norm-sorted tensor layout for byte storage with d <= 128 (topk_tc.cuh)
+    // norm-sorted tensor layout for byte storage with d <= 128 (topk_tc.cu)
     unsigned char* t_rows = nullptr;
     int32_t* t_norms = nullptr;
     uint32_t* t_ids = nullptr;
@@ -107,8 +109,8 @@ int odd16_pitch(int row_bytes) {
     return p;
 }
 
-int check_launch(gpann_ctx* ctx, const char* what) {
-    ctx->launches++;
+int check_launch(gpann_ctx* ctx, const char* what, int count = 1) {
+    ctx->launches += count;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, GPANN_E_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
     return 0;
@@ -120,11 +122,28 @@ int log2_ceil(size_t x) {
     return b;
 }
 
+int blocks_for(gpann_ctx* ctx, size_t items, int per_block = 256, int waves = 16) {
+    return (int) std::max<size_t>(1, std::min<size_t>((items + per_block - 1) / per_block, (size_t) ctx->num_sms * waves));
+}
+
+int encode_rows_map(gpann_ctx* ctx, CUtensorMap* map, void* base, size_t rows, int box_rows, const char* what) {
+    const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) rows };
+    const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
+    const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(ctx, GPANN_E_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int) r));
+    return 0;
+}
+
 // ---- tensor layout for byte rows ---------------------------------------------------------------------------
 int build_tensor_bytes(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
     const size_t n = pts->n;
     const int d = (int) pts->d;
-    if (n == 0 || d > tc::kRowBytes || n > 0xFFFFFF00ull) return 0;
+    if (n == 0 || d > tc::kRowBytes || n > 0x7FFFFF00ull) return 0;
     if (!ctx->encode_tiled) return 0;
     const size_t n_pad = ((n + tc::kTileN - 1) / tc::kTileN) * tc::kTileN;
     uint32_t *norms = nullptr, *index = nullptr, *norms_sorted = nullptr, *perm = nullptr;
@@ -140,36 +159,30 @@ int build_tensor_bytes(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
         return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory");
     }
     const int is_signed = pts->storage == GPANN_STORAGE_S8;
-    const int blocks = (int) std::min<size_t>((n + 255) / 256, (size_t) ctx->num_sms * 16);
-    byte_norms_kernel<<<blocks, 256, 0, st>>>((const unsigned char*) pts->rows, n, d, pts->pitch, is_signed, norms, index);
+    launch_byte_norms((const unsigned char*) pts->rows, n, d, pts->pitch, is_signed, norms, index, blocks_for(ctx, n), st);
     GP_TRY(check_launch(ctx, "byte_norms_kernel"));
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, norms, norms_sorted, index, perm, (int) n, 0, 25, st);
+    sort_pairs_u32(nullptr, tmp_bytes, norms, norms_sorted, index, perm, n, 25, st);
     if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) {
         cleanup();
         return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (sort)");
     }
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, norms, norms_sorted, index, perm, (int) n, 0, 25, st);
+    if (sort_pairs_u32(tmp, tmp_bytes, norms, norms_sorted, index, perm, n, 25, st) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_CUDA, "build_tensor_bytes: radix sort failed");
+    }
     ctx->launches += 4;
     if (cudaMalloc(&pts->t_rows, n_pad * tc::kRowBytes) != cudaSuccess || cudaMalloc(&pts->t_norms, n_pad * 4) != cudaSuccess ||
         cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess) {
         cleanup();
         return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (layout)");
     }
-    const int gblocks = (int) std::min<size_t>((n_pad * 32 + 255) / 256, (size_t) ctx->num_sms * 32);
-    gather_sorted_rows_kernel<<<gblocks, 256, 0, st>>>((const unsigned char*) pts->rows, n, d, pts->pitch, perm, norms_sorted,
-                                                       pts->id_base, n_pad, pts->t_rows, pts->t_norms, pts->t_ids);
+    launch_gather_sorted_rows((const unsigned char*) pts->rows, n, d, pts->pitch, perm, norms_sorted, pts->id_base, n_pad,
+                              pts->t_rows, pts->t_norms, pts->t_ids, blocks_for(ctx, n_pad * 32, 256, 32), st);
     GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     cleanup();
     pts->n_pad = n_pad;
-    const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) n_pad };
-    const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
-    const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) tc::kTileN };
-    const cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = ctx->encode_tiled(&pts->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, pts->t_rows, gdim, gstride, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, GPANN_E_CUDA, "cuTensorMapEncodeTiled(points) failed: " + std::to_string((int) r));
+    GP_TRY(encode_rows_map(ctx, &pts->tmap, pts->t_rows, n_pad, tc::kTileN, "points"));
     pts->has_tensor = true;
     return 0;
 }
@@ -181,12 +194,13 @@ struct TopkOut {
     uint32_t* id = nullptr;    // device [nq,k]
     uint32_t* count = nullptr; // device [nq]
     float* kth = nullptr;      // device [nq]
+    int kth_full_only = 0;
 };
 
-int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_stride, size_t q_offset, size_t nq, int k,
-                 const TopkOut& o, size_t out_q_offset, cudaStream_t st) {
+int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_stride, size_t nq, int k, const TopkOut& o,
+                 size_t out_q_offset, cudaStream_t st) {
     MergeParams mp;
-    mp.keys = keys + q_offset * k;
+    mp.keys = keys;
     mp.parts = parts;
     mp.nq = nq;
     mp.nq_stride = nq_stride;
@@ -197,15 +211,10 @@ int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_s
     mp.out_keys = o.keys ? o.keys + out_q_offset * k : nullptr;
     mp.out_count = o.count ? o.count + out_q_offset : nullptr;
     mp.out_kth = o.kth ? o.kth + out_q_offset : nullptr;
+    mp.kth_full_only = o.kth_full_only;
     const size_t smem = (size_t) 4 * mp.cap * sizeof(uint64_t);
-    merge_keys_kernel<<<(unsigned) ((nq + 3) / 4), 128, smem, st>>>(mp);
+    launch_merge_keys(mp, (unsigned) ((nq + 3) / 4), smem, st);
     return check_launch(ctx, "merge_keys_kernel");
-}
-
-template <int STORAGE>
-int launch_stream_t(gpann_ctx* ctx, const StreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    topk_stream_kernel<STORAGE><<<grid, kStreamTile, smem, st>>>(p);
-    return check_launch(ctx, "topk_stream_kernel");
 }
 
 int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
@@ -237,7 +246,8 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     const size_t budget = 160 * 1024;
     if (tile_bytes + per_q > 200 * 1024)
         return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile");
-    int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16), std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
+    const int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16),
+                                          std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
     p.qb = qb;
     const size_t smem = tile_bytes + (size_t) qb * per_q;
     const size_t nrows = row_end - row_begin;
@@ -247,15 +257,19 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     const unsigned gy = (unsigned) ((nq + qb - 1) / qb);
     GP_TRY(reserve(ctx, ctx->partial, (size_t) gx * nq * k * sizeof(uint64_t)));
     p.partial = (uint64_t*) ctx->partial.p;
-    int r;
-    if (pts->storage == GPANN_STORAGE_F32) r = launch_stream_t<kF32>(ctx, p, dim3(gx, gy), smem, st);
-    else if (pts->storage == GPANN_STORAGE_U8) r = launch_stream_t<kU8>(ctx, p, dim3(gx, gy), smem, st);
-    else r = launch_stream_t<kS8>(ctx, p, dim3(gx, gy), smem, st);
-    GP_TRY(r);
+    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+    launch_topk_stream(p, dim3(gx, gy), smem, st);
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev1, st);
+        ctx->timed = true;
+    }
+    GP_TRY(check_launch(ctx, "topk_stream_kernel"));
     ctx->last_algo = "stream";
-    return launch_merge(ctx, p.partial, gx, nq, 0, nq, k, out, 0, st);
+    return launch_merge(ctx, p.partial, gx, nq, nq, k, out, 0, st);
 }
 
+// The tcgen05 path for byte storage.  *queries_ok_host = 0 (and nothing written) when the queries are not
+// integer-valued in the storage's range; the caller then takes the exact float scan.
 int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
                       cudaStream_t st, int* queries_ok_host) {
     const int is_signed = pts->storage == GPANN_STORAGE_S8;
@@ -264,7 +278,8 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
     *queries_ok_host = 1;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
         const size_t nqb = std::min(batch_max, nq - q0);
-        const int R = (int) std::min<size_t>(tc::kMaxR, (nqb + tc::kTileM - 1) / tc::kTileM);
+        // R (Q tiles resident per CTA) is 2 or 4: even, so that each query is owned by one epilogue thread
+        const int R = nqb > 2 * (size_t) tc::kTileM ? 4 : 2;
         const int G = (int) ((nqb + (size_t) R * tc::kTileM - 1) / ((size_t) R * tc::kTileM));
         const uint32_t tiles_total = (uint32_t) (pts->n_pad / tc::kTileN);
         const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / G), tiles_total));
@@ -272,14 +287,14 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
         const int cap = std::max(128, pow2_ceil(k + 64));
         GP_TRY(reserve(ctx, ctx->qrows, nq_pad * tc::kRowBytes));
         GP_TRY(reserve(ctx, ctx->qnorm, nq_pad * 4));
+        GP_TRY(reserve(ctx, ctx->bound, nq_pad * 4));
         GP_TRY(reserve(ctx, ctx->flags, 64));
         GP_TRY(reserve(ctx, ctx->cand, (size_t) G * S * R * tc::kTileM * cap * sizeof(uint64_t)));
         GP_TRY(reserve(ctx, ctx->partial, (size_t) S * nq_pad * k * sizeof(uint64_t)));
         int one = 1;
         CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
-        prep_queries_bytes_kernel<<<(unsigned) std::min<size_t>((nq_pad * 32 + 255) / 256, 1024), 256, 0, st>>>(
-            dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p, (int32_t*) ctx->qnorm.p,
-            (int*) ctx->flags.p);
+        launch_prep_queries_bytes(dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p,
+                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
         GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
         int ok = 0;
         CU_TRY(ctx, cudaMemcpyAsync(&ok, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
@@ -289,14 +304,7 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
             return 0;
         }
         CUtensorMap tmap_q;
-        const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) nq_pad };
-        const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
-        const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) tc::kTileM };
-        const cuuint32_t estr[2] = { 1, 1 };
-        CUresult cr = ctx->encode_tiled(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->qrows.p, gdim, gstride, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return fail(ctx, GPANN_E_CUDA, "cuTensorMapEncodeTiled(queries) failed: " + std::to_string((int) cr));
+        GP_TRY(encode_rows_map(ctx, &tmap_q, ctx->qrows.p, nq_pad, tc::kTileM, "queries"));
         tc::Args a;
         a.pnorm = pts->t_norms;
         a.pid = pts->t_ids;
@@ -307,14 +315,38 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
         a.nks = (d + 31) / 32;
         a.k = k;
         a.cap = cap;
-        a.tiles_total = tiles_total;
         a.idesc = tc::make_idesc_i8(is_signed);
         a.cand = (uint64_t*) ctx->cand.p;
         a.partial = (uint64_t*) ctx->partial.p;
+        a.bound = (uint32_t*) ctx->bound.p;
         a.mode = ctx->tc_mode;
-        tc::topk_tc_bytes_kernel<<<G * S, tc::kThreads, tc::smem_bytes(R), st>>>(pts->tmap, tmap_q, a);
+        const unsigned grid = (unsigned) (G * S);
+        const size_t smem = tc::smem_bytes(R);
+        // Pre-pass over a strided sample of tiles: its k-th distances are valid upper bounds on the final ones and
+        // let every CTA of the main pass start with a tight filter threshold instead of a cold one.
+        const uint32_t sample_per_split = 12;
+        if (ctx->tc_prepass && ctx->tc_mode == 0 && tiles_total >= 64u * (uint32_t) S * sample_per_split) {
+            a.ntiles = (uint32_t) S * sample_per_split;
+            a.tile_stride = tiles_total / a.ntiles;
+            a.tile_lo = a.tile_stride / 2;
+            launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
+            GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel(sample)"));
+            TopkOut b;
+            b.kth = (float*) ctx->bound.p;  // float bits: read back by the kernel as the bound
+            b.kth_full_only = 1;
+            GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, b, 0, st));
+        }
+        a.tile_lo = 0;
+        a.tile_stride = 1;
+        a.ntiles = tiles_total;
+        if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+        launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev1, st);
+            ctx->timed = true;
+        }
         GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel"));
-        GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, 0, nqb, k, out, q0, st));
+        GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, out, q0, st));
     }
     ctx->last_algo = pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8";
     return 0;
@@ -345,7 +377,7 @@ int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, siz
         CU_TRY(ctx, cudaMemcpyAsync(ctx->partial.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
         ctx->last_algo = "empty";
-        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, nq, 0, nq, k, out, 0, st);
+        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, nq, nq, k, out, 0, st);
     }
     return topk_stream(ctx, pts, row_begin, row_end, dq, nq, k, metric, out, st);
 }
@@ -386,15 +418,7 @@ RowsView rows_view(const gpann_points* pts) {
     v.storage = pts->storage;
     v.d = (int) pts->d;
     v.n = pts->n;
-    v.ids = nullptr;
-    v.id_base = 0;
     return v;
-}
-
-template <int STORAGE>
-int launch_assign_t(gpann_ctx* ctx, const AssignParams& p, unsigned grid, size_t smem, cudaStream_t st) {
-    kmeans_assign_kernel<STORAGE><<<grid, kStreamTile, smem, st>>>(p);
-    return check_launch(ctx, "kmeans_assign_kernel");
 }
 
 int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric,
@@ -420,9 +444,8 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
     const size_t ntiles = (pts->n + kStreamTile - 1) / kStreamTile;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const unsigned grid = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
-    if (pts->storage == GPANN_STORAGE_F32) return launch_assign_t<kF32>(ctx, p, grid, smem, st);
-    if (pts->storage == GPANN_STORAGE_U8) return launch_assign_t<kU8>(ctx, p, grid, smem, st);
-    return launch_assign_t<kS8>(ctx, p, grid, smem, st);
+    launch_kmeans_assign(p, grid, smem, st);
+    return check_launch(ctx, "kmeans_assign_kernel");
 }
 
 // sums [kc,d] (optionally normalised) and counts [kc] of the points assigned to each cluster, fixed order.
@@ -440,19 +463,19 @@ int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* 
     uint32_t* keys_out = (uint32_t*) ctx->sort_b.p;
     uint32_t* idx_in = (uint32_t*) ctx->sort_c.p;
     uint32_t* idx_out = (uint32_t*) ctx->sort_d.p;
-    const int blocks = (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t) ctx->num_sms * 16));
-    histogram_keys_kernel<<<blocks, 256, 0, st>>>(d_assign, n, (int) kc, (unsigned long long*) d_counts, keys_in, idx_in);
+    launch_histogram_keys(d_assign, n, (int) kc, (unsigned long long*) d_counts, keys_in, idx_in, blocks_for(ctx, n), st);
     GP_TRY(check_launch(ctx, "histogram_keys_kernel"));
     const int bits = std::max(1, log2_ceil(kc + 1));
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, idx_in, idx_out, (int) n, 0, bits, st);
+    sort_pairs_u32(nullptr, tmp_bytes, keys_in, keys_out, idx_in, idx_out, n, bits, st);
     GP_TRY(reserve(ctx, ctx->sort_tmp, tmp_bytes));
-    cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, keys_in, keys_out, idx_in, idx_out, (int) n, 0, bits, st);
+    if (sort_pairs_u32(ctx->sort_tmp.p, tmp_bytes, keys_in, keys_out, idx_in, idx_out, n, bits, st) != cudaSuccess)
+        return fail(ctx, GPANN_E_CUDA, "kmeans: radix sort failed");
     ctx->launches += 3;
     GP_TRY(reserve(ctx, ctx->misc, (kc + 1) * 4 + (kc + 1) * 8 + 64));
     uint64_t* member_begin = (uint64_t*) ctx->misc.p;
     uint32_t* seg_begin = (uint32_t*) (member_begin + kc + 1);
-    cluster_segments_kernel<<<1, 32, 0, st>>>(d_counts, (int) kc, seg_begin, member_begin);
+    launch_cluster_segments(d_counts, (int) kc, seg_begin, member_begin, st);
     GP_TRY(check_launch(ctx, "cluster_segments_kernel"));
     const size_t max_segs = n / kSegRows + kc + 1;
     GP_TRY(reserve(ctx, ctx->segsums, max_segs * d * 4));
@@ -463,11 +486,9 @@ int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* 
     rp.member_begin = member_begin;
     rp.kc = (int) kc;
     rp.seg_sums = (float*) ctx->segsums.p;
-    if (pts->storage == GPANN_STORAGE_F32) cluster_reduce_segments_kernel<kF32><<<(unsigned) max_segs, 256, 0, st>>>(rp);
-    else if (pts->storage == GPANN_STORAGE_U8) cluster_reduce_segments_kernel<kU8><<<(unsigned) max_segs, 256, 0, st>>>(rp);
-    else cluster_reduce_segments_kernel<kS8><<<(unsigned) max_segs, 256, 0, st>>>(rp);
+    launch_cluster_reduce_segments(rp, (unsigned) max_segs, st);
     GP_TRY(check_launch(ctx, "cluster_reduce_segments_kernel"));
-    cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(rp.seg_sums, seg_begin, d_counts, (int) kc, d, normalize, d_out);
+    launch_cluster_finalize(rp.seg_sums, seg_begin, d_counts, (int) kc, d, normalize, d_out, st);
     return check_launch(ctx, "cluster_finalize_kernel");
 }
 
@@ -493,7 +514,8 @@ int gpann_init(gpann_ctx** out, int device) {
     if (!ctx) return GPANN_E_OOM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return GPANN_E_CUDA;
     }
@@ -502,30 +524,17 @@ int gpann_init(gpann_ctx** out, int device) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
         ctx->encode_tiled = (EncodeTiledFn) fn;
-    {
-        // opt every large-shared-memory kernel in for this device (attributes are per device)
-        const int big = 200 * 1024;
-        bool ok = true;
-        ok &= cudaFuncSetAttribute(topk_stream_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(topk_stream_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(topk_stream_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(kmeans_assign_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(objective_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(objective_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(objective_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(tc::topk_tc_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) tc::smem_bytes(tc::kMaxR)) == cudaSuccess;
-        if (!ok) {
-            std::fprintf(stderr, "gpann_init: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
-            cudaStreamDestroy(ctx->stream);
-            delete ctx;
-            return GPANN_E_CUDA;
-        }
+    // opt every large-shared-memory kernel in for this device (function attributes are per device)
+    if (stream_set_attributes() != cudaSuccess || kmeans_set_attributes() != cudaSuccess || tc_set_attributes() != cudaSuccess) {
+        std::fprintf(stderr, "gpann_init: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return GPANN_E_CUDA;
     }
     const char* mode = std::getenv("GPANN_TC_MODE");
     ctx->tc_mode = mode ? std::atoi(mode) : 0;
+    const char* pre = std::getenv("GPANN_TC_PREPASS");
+    ctx->tc_prepass = pre ? std::atoi(pre) : 1;
     *out = ctx;
     return 0;
 }
@@ -534,11 +543,13 @@ void gpann_destroy(gpann_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->flags, &ctx->keys_out, &ctx->dist_out,
+    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign };
     for (DevBuf* b : bufs) release(*b);
     cudaStreamDestroy(ctx->stream);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
     delete ctx;
 }
 
@@ -550,6 +561,18 @@ int gpann_set_algo(gpann_ctx* ctx, int algo) {
     return 0;
 }
 uint64_t gpann_launch_count(const gpann_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int gpann_set_timing(gpann_ctx* ctx, int on) {
+    if (!ctx) return GPANN_E_ARG;
+    ctx->timing = on ? 1 : 0;
+    ctx->timed = false;
+    return 0;
+}
+float gpann_last_kernel_ms(gpann_ctx* ctx) {
+    if (!ctx || !ctx->timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
 const char* gpann_last_algo(const gpann_ctx* ctx) { return ctx ? ctx->last_algo : "none"; }
 
 static int finish_points(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st, gpann_points** out) {
@@ -586,8 +609,7 @@ int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t
         int flags_h[2] = { 1, 1 };
         GP_TRY(reserve(ctx, ctx->flags, 64));
         CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, flags_h, 8, cudaMemcpyHostToDevice, st));
-        const int blocks = (int) std::min<size_t>((n * d + 255) / 256, (size_t) ctx->num_sms * 16);
-        detect_bytes_kernel<<<blocks, 256, 0, st>>>(d_f32, n * d, (int*) ctx->flags.p);
+        launch_detect_bytes(d_f32, n * d, (int*) ctx->flags.p, blocks_for(ctx, n * d), st);
         GP_TRY(check_launch(ctx, "detect_bytes_kernel"));
         CU_TRY(ctx, cudaMemcpyAsync(flags_h, ctx->flags.p, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -617,8 +639,7 @@ int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t
             return fail(ctx, GPANN_E_OOM, "points_upload: out of device memory");
         }
         if (n) {
-            const int blocks = (int) std::min<size_t>((n * d + 255) / 256, (size_t) ctx->num_sms * 16);
-            narrow_rows_kernel<<<blocks, 256, 0, st>>>(d_f32, n, (int) d, (int) d, bytes);
+            launch_narrow_rows(d_f32, n, (int) d, (int) d, bytes, blocks_for(ctx, n * d), st);
             ctx->launches++;
         }
         cudaStreamSynchronize(st);
@@ -680,7 +701,7 @@ int gpann_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, siz
     pts->rows = const_cast<void*>(dev_rows);  // borrowed: the caller keeps the rows alive
     pts->owns_rows = false;
     pts->pitch = storage == GPANN_STORAGE_F32 ? d * 4 : d;
-    return finish_points(ctx, pts, stream ? (cudaStream_t) stream : ctx->stream, out);
+    return finish_points(ctx, pts, (cudaStream_t) stream, out);
 }
 
 void gpann_points_free(gpann_points* pts) {
@@ -724,7 +745,7 @@ int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     TopkOut o;
     o.keys = dev_out_keys;
-    return topk_dispatch(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, stream ? (cudaStream_t) stream : ctx->stream);
+    return topk_dispatch(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, (cudaStream_t) stream);
 }
 
 int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist,
@@ -737,7 +758,7 @@ int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t par
     o.dist = dev_out_dist;
     o.id = dev_out_id;
     o.keys = dev_out_keys;
-    return launch_merge(ctx, dev_keys, parts, nq, 0, nq, k, o, 0, stream ? (cudaStream_t) stream : ctx->stream);
+    return launch_merge(ctx, dev_keys, parts, nq, nq, k, o, 0, (cudaStream_t) stream);
 }
 
 uint64_t gpann_pack_key(float dist, uint32_t id) { return pack_key(dist, id); }
@@ -775,7 +796,7 @@ int gpann_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const f
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
     if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t) stream;
     int32_t* d_assign = dev_out_assign;
     if (!d_assign) {
         GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(pts->n, 1) * 4));
@@ -850,12 +871,8 @@ int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centro
     GP_TRY(reserve(ctx, ctx->misc, (size_t) grid * 8 + 64));
     p.block_sums = (double*) ctx->misc.p;
     double* d_out = p.block_sums + grid;
-    if (pts->storage == GPANN_STORAGE_F32) objective_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
-    else if (pts->storage == GPANN_STORAGE_U8) objective_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
-    else objective_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
-    GP_TRY(check_launch(ctx, "objective_kernel"));
-    objective_final_kernel<<<1, 32, 0, st>>>(p.block_sums, (int) grid, d_out);
-    GP_TRY(check_launch(ctx, "objective_final_kernel"));
+    launch_objective(p, grid, smem, d_out, st);
+    GP_TRY(check_launch(ctx, "objective_kernel", 2));
     CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     return 0;

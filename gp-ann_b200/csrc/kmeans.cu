@@ -1,4 +1,4 @@
-// kmeans.cuh -- k-means form of the hot path, exact (reference arithmetic order) CUDA-core kernels.
+// kmeans.cu -- k-means form of the hot path, exact (reference arithmetic order) CUDA-core kernels.
 //
 //   kmeans_assign_kernel   NearestCenters / Top1Neighbor      (reference src/kmeans.cpp:12-27)
 //   cluster_reduce_*       SumPointsInClustersL2 / Aggregate*  (src/kmeans.cpp:116-204), deterministic order
@@ -9,21 +9,13 @@
 // cluster are brought together by a STABLE radix sort of (assignment, point index) pairs, cut into segments
 // of kSegRows rows, summed by one CTA per segment in a fixed order, and the segment sums are added per
 // cluster in segment order -- bitwise reproducible run to run and independent of the grid.
-#pragma once
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
-#include "stream.cuh"
+#include "distance.cuh"
+#include "params.h"
 
 namespace gpann {
-
-struct RowsView {
-    const char* rows;
-    size_t pitch;
-    int storage;
-    int d;
-    size_t n;
-    const uint32_t* ids;  // optional (norm-sorted layouts): original row index = ids[row] - id_base
-    uint32_t id_base;
-};
 
 template <int STORAGE>
 __device__ __forceinline__ void stage_rows(const RowsView& v, size_t r0, int rows_here, unsigned char* s_rows, int spitch,
@@ -45,16 +37,6 @@ __device__ __forceinline__ void stage_rows(const RowsView& v, size_t r0, int row
         }
     }
 }
-
-struct AssignParams {
-    RowsView pts;
-    const float* centroids;  // [kc, d]
-    int kc, metric;
-    int cchunk;              // centroids staged per shared-memory chunk
-    int spitch, qpitch, vec_ok;
-    int32_t* out_assign;     // [n] indexed by original row
-    float* out_mindist;      // optional [n]
-};
 
 // One thread per point, centroids streamed through shared memory in chunks; strict '<' keeps the lowest
 // centroid index on ties, -1 if nothing is below FLT_MAX (src/kmeans.cpp:12-23).
@@ -93,17 +75,13 @@ __global__ void __launch_bounds__(kStreamTile) kmeans_assign_kernel(const Assign
         }
         if (tid < rows_here) {
             const size_t row = r0 + tid;
-            const size_t orig = p.pts.ids ? (size_t) (p.pts.ids[row] - p.pts.id_base) : row;
-            if (!p.pts.ids || p.pts.ids[row] != kInvalidId) {
-                p.out_assign[orig] = best;
-                if (p.out_mindist) p.out_mindist[orig] = best_dist;
-            }
+            p.out_assign[row] = best;
+            if (p.out_mindist) p.out_mindist[row] = best_dist;
         }
     }
 }
 
 // ---- deterministic per-cluster sums --------------------------------------------------------------------
-constexpr int kSegRows = 1024;  // rows per reduction segment
 
 // counts[c] = number of members; seg_begin[c] = first segment index of cluster c (exclusive scan of
 // ceil(count/kSegRows)); seg_begin[kc] = total.  Single CTA, kc <= a few thousand.
@@ -133,15 +111,6 @@ __global__ void histogram_keys_kernel(const int32_t* assign, size_t n, int kc, u
         index[i] = (uint32_t) i;
     }
 }
-
-struct ReduceParams {
-    RowsView pts;               // rows addressed by ORIGINAL index when ids == nullptr
-    const uint32_t* members;    // point rows sorted (stably) by cluster
-    const uint32_t* seg_begin;  // [kc+1]
-    const uint64_t* member_begin;  // [kc+1]
-    int kc;
-    float* seg_sums;            // [total_segments, d]
-};
 
 // One CTA per segment: thread t owns dimension j = t % dpad and row slot t / dpad; slots are added in order.
 template <int STORAGE>
@@ -203,14 +172,6 @@ __global__ void normalize_centroids_kernel(float* sums, const uint64_t* counts, 
     for (int j = threadIdx.x; j < d; j += blockDim.x) sums[(size_t) c * d + j] = sums[(size_t) c * d + j] / (float) counts[c];
 }
 
-struct ObjectiveParams {
-    RowsView pts;
-    const float* centroids;
-    const int32_t* assign;  // by original row
-    int kc, metric, spitch, vec_ok;
-    double* block_sums;     // [gridDim.x]
-};
-
 // sum_i pos_distance(P_i, C_{a_i}) with every f32 term widened to double (src/kmeans.cpp:246-249); fixed-order
 // two-level reduction (per-CTA partials, summed in CTA order by objective_final_kernel).
 template <int STORAGE>
@@ -229,10 +190,8 @@ __global__ void __launch_bounds__(kStreamTile) objective_kernel(const ObjectiveP
         __syncthreads();
         if (tid < rows_here) {
             const size_t row = r0 + tid;
-            const bool valid = !p.pts.ids || p.pts.ids[row] != kInvalidId;
-            if (valid) {
-                const size_t orig = p.pts.ids ? (size_t) (p.pts.ids[row] - p.pts.id_base) : row;
-                const int c = p.assign[orig];
+            {
+                const int c = p.assign[row];
                 const char* myrow = reinterpret_cast<const char*>(s_rows) + (size_t) tid * p.spitch;
                 const float* cen = p.centroids + (size_t) c * p.pts.d;
                 float dist;
@@ -261,6 +220,49 @@ __global__ void objective_final_kernel(const double* block_sums, int nblocks, do
         for (int i = 0; i < nblocks; ++i) t += block_sums[i];
         *out = t;
     }
+}
+
+cudaError_t kmeans_set_attributes() {
+    const int big = 200 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(kmeans_assign_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kmeans_assign_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kmeans_assign_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(objective_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(objective_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(objective_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    return e;
+}
+
+void launch_kmeans_assign(const AssignParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+    if (p.pts.storage == kF32) kmeans_assign_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
+    else if (p.pts.storage == kU8) kmeans_assign_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
+    else kmeans_assign_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
+}
+void launch_histogram_keys(const int32_t* assign, size_t n, int kc, unsigned long long* counts, uint32_t* keys, uint32_t* index,
+                           int blocks, cudaStream_t st) {
+    histogram_keys_kernel<<<blocks, 256, 0, st>>>(assign, n, kc, counts, keys, index);
+}
+void launch_cluster_segments(const uint64_t* counts, int kc, uint32_t* seg_begin, uint64_t* member_begin, cudaStream_t st) {
+    cluster_segments_kernel<<<1, 32, 0, st>>>(counts, kc, seg_begin, member_begin);
+}
+void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaStream_t st) {
+    if (p.pts.storage == kF32) cluster_reduce_segments_kernel<kF32><<<grid, 256, 0, st>>>(p);
+    else if (p.pts.storage == kU8) cluster_reduce_segments_kernel<kU8><<<grid, 256, 0, st>>>(p);
+    else cluster_reduce_segments_kernel<kS8><<<grid, 256, 0, st>>>(p);
+}
+void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d, int normalize,
+                             float* out, cudaStream_t st) {
+    cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(seg_sums, seg_begin, counts, kc, d, normalize, out);
+}
+void launch_objective(const ObjectiveParams& p, unsigned grid, size_t smem, double* d_out, cudaStream_t st) {
+    if (p.pts.storage == kF32) objective_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
+    else if (p.pts.storage == kU8) objective_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
+    else objective_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
+    objective_final_kernel<<<1, 32, 0, st>>>(p.block_sums, (int) grid, d_out);
+}
+cudaError_t sort_pairs_u32(void* tmp, size_t& tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                           uint32_t* vals_out, size_t n, int bits, cudaStream_t st) {
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int) n, 0, bits, st);
 }
 
 }  // namespace gpann

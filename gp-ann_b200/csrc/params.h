@@ -1,0 +1,160 @@
+// params.h -- plain parameter structs and tile constants shared by the kernels (.cu) and the host ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace gpann {
+
+constexpr int kStreamTile = 128;  // points per tile == threads per CTA of the CUDA-core kernels
+constexpr int kSegRows = 1024;    // rows per deterministic-reduction segment (k-means sums)
+
+// ---- stream.cu ----------------------------------------------------------------------------------------------
+struct StreamParams {
+    const char* rows;       // first row of the point set
+    size_t pitch;           // bytes between rows
+    int storage;            // kF32 / kU8 / kS8
+    int d;
+    size_t row_begin, row_end;  // scanned row range
+    const uint32_t* ids;    // optional per-row ids; else id = id_base + row
+    uint32_t id_base;
+    uint32_t id_lo, id_hi;  // keep only ids in [id_lo, id_hi)
+    const float* queries;   // [nq, d]
+    int nq, k, metric;
+    int qb;                 // queries per batch (blockIdx.y selects the batch)
+    int cap;                // candidate buffer capacity per query (power of two, >= k + kStreamTile)
+    int spitch;             // shared-memory row pitch in bytes (odd multiple of 16)
+    int qpitch;             // shared-memory query pitch in floats (multiple of 4)
+    int vec_ok;             // rows can be fetched with 16-byte loads
+    uint64_t* partial;      // [gridDim.x, nq, k]
+};
+
+struct MergeParams {
+    const uint64_t* keys;   // [parts, nq_stride, k]
+    size_t parts, nq;
+    size_t nq_stride;       // queries per part in `keys` (>= nq: padded layouts)
+    int k;
+    int cap;                // power of two >= 2k: selection window
+    float* out_dist;
+    uint32_t* out_id;
+    uint64_t* out_keys;
+    uint32_t* out_count;
+    float* out_kth;
+    int kth_full_only;      // out_kth = +inf unless k valid keys were found (a bound must come from a full list)
+};
+
+// ---- kmeans.cu ----------------------------------------------------------------------------------------------
+struct RowsView {
+    const char* rows;
+    size_t pitch;
+    int storage;
+    int d;
+    size_t n;
+};
+
+struct AssignParams {
+    RowsView pts;
+    const float* centroids;  // [kc, d]
+    int kc, metric;
+    int cchunk;              // centroids staged per shared-memory chunk
+    int spitch, qpitch, vec_ok;
+    int32_t* out_assign;     // [n]
+    float* out_mindist;      // optional [n]
+};
+
+struct ReduceParams {
+    RowsView pts;
+    const uint32_t* members;       // point rows sorted (stably) by cluster
+    const uint32_t* seg_begin;     // [kc+1]
+    const uint64_t* member_begin;  // [kc+1]
+    int kc;
+    float* seg_sums;               // [total_segments, d]
+};
+
+struct ObjectiveParams {
+    RowsView pts;
+    const float* centroids;
+    const int32_t* assign;
+    int kc, metric, spitch, vec_ok;
+    double* block_sums;  // [gridDim.x]
+};
+
+// ---- topk_tc.cu ---------------------------------------------------------------------------------------------
+namespace tc {
+constexpr int kTileN = 256;       // points per tile  (UMMA N)
+constexpr int kTileM = 128;       // queries per tile (UMMA M)
+constexpr int kRowBytes = 128;    // operand row bytes = one SWIZZLE_128B row
+constexpr int kStages = 3;
+constexpr int kMaxR = 4;
+constexpr int kEpiWarps = 8;                     // filter warps (two groups of 4, one per TMEM accumulator slot)
+constexpr int kSelWarps = 2;                     // selection warps (own the per-query top-k lists)
+constexpr int kQueueCap = 1024;                  // records per candidate queue (one queue per selection warp)
+constexpr int kThreads = 64 + 32 * (kEpiWarps + kSelWarps);  // warp 0: TMA, warp 1: MMA, epilogue, selection
+constexpr int kQTileBytes = kTileM * kRowBytes;  // 16 KB
+constexpr int kPTileBytes = kTileN * kRowBytes;  // 32 KB
+constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
+
+struct Args {
+    const int32_t* pnorm;    // [n_pad] ascending
+    const uint32_t* pid;     // [n_pad] original ids, kInvalidId on padding rows
+    const int32_t* qnorm;    // [G*R*128]
+    int R, G, S;             // Q tiles per CTA (2 or 4), query groups, point splits
+    int nks;                 // K steps of 32 bytes
+    int k, cap;              // top-k and candidate buffer capacity (power of two >= k + 64)
+    uint32_t tile_lo, tile_stride, ntiles;  // this launch scans tiles tile_lo + i*tile_stride, i in [0,ntiles)
+    uint32_t idesc;          // tcgen05 instruction descriptor
+    uint64_t* cand;          // [grid, R*128, cap] per-query key lists (global, touched by the selection warps only)
+    uint64_t* partial;       // [S, G*R*128, k]
+    uint32_t* bound;         // [G*R*128] shared upper bound on each query's kth distance (ordered-float bits)
+    int mode;                // 0 = full; probes with invalid results: 1 = MMA + TMEM loads + max, 2 = MMA issue only
+};
+
+// Shared-memory footprint for R resident Q tiles (+1 KB so the operand area can be aligned to 1024 bytes).
+inline size_t smem_bytes(int R) {
+    return 1024 + (size_t) R * kQTileBytes + (size_t) kStages * kPTileBytes + 256 /*barriers, counters*/ +
+           (size_t) kStages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * kQueueCap * 12 /*queues*/ +
+           (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/;
+}
+inline uint32_t make_idesc_i8(bool is_signed) {
+    const uint32_t fmt = is_signed ? 1u : 0u;
+    return (2u << 4)                    // D format: S32
+           | (fmt << 7) | (fmt << 10)   // A, B format: 0 = u8, 1 = s8
+           | ((uint32_t) (kTileN >> 3) << 17) | ((uint32_t) (kTileM >> 4) << 24);  // both operands K-major
+}
+}  // namespace tc
+
+// ---- launchers (each defined in the translation unit that owns the kernel) -------------------------------------
+cudaError_t stream_set_attributes();
+cudaError_t kmeans_set_attributes();
+cudaError_t tc_set_attributes();
+
+void launch_topk_stream(const StreamParams& p, dim3 grid, size_t smem, cudaStream_t st);
+void launch_merge_keys(const MergeParams& p, unsigned grid, size_t smem, cudaStream_t st);
+
+void launch_kmeans_assign(const AssignParams& p, unsigned grid, size_t smem, cudaStream_t st);
+void launch_histogram_keys(const int32_t* assign, size_t n, int kc, unsigned long long* counts, uint32_t* keys,
+                           uint32_t* index, int blocks, cudaStream_t st);
+void launch_cluster_segments(const uint64_t* counts, int kc, uint32_t* seg_begin, uint64_t* member_begin, cudaStream_t st);
+void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaStream_t st);
+void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d,
+                             int normalize, float* out, cudaStream_t st);
+void launch_objective(const ObjectiveParams& p, unsigned grid, size_t smem, double* d_out, cudaStream_t st);
+// stable radix sort of (key, value) pairs on the low `bits` bits; tmp == nullptr only queries tmp_bytes
+cudaError_t sort_pairs_u32(void* tmp, size_t& tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                           uint32_t* vals_out, size_t n, int bits, cudaStream_t st);
+
+void launch_detect_bytes(const float* x, size_t count, int* flags, int blocks, cudaStream_t st);
+void launch_narrow_rows(const float* x, size_t n, int d, int pitch, unsigned char* out, int blocks, cudaStream_t st);
+void launch_byte_norms(const unsigned char* rows, size_t n, int d, size_t pitch, int is_signed, uint32_t* norms, uint32_t* index,
+                       int blocks, cudaStream_t st);
+void launch_gather_sorted_rows(const unsigned char* rows, size_t n, int d, size_t pitch, const uint32_t* perm,
+                               const uint32_t* sorted_norms, uint32_t id_base, size_t n_pad, unsigned char* out_rows,
+                               int32_t* out_norms, uint32_t* out_ids, int blocks, cudaStream_t st);
+void launch_prep_queries_bytes(const float* q, int nq, int d, int nq_pad, int is_signed, unsigned char* out_rows,
+                               int32_t* out_norms, int* ok, uint32_t* bound, cudaStream_t st);
+
+void launch_topk_tc_bytes(const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid, size_t smem,
+                          cudaStream_t st);
+
+}  // namespace gpann

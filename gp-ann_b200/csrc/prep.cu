@@ -1,8 +1,8 @@
-// prep.cuh -- one-time data preparation kernels: storage detection/narrowing (the reference's reader widens
+// prep.cu -- one-time data preparation kernels: storage detection/narrowing (the reference's reader widens
 // .u8bin/.i8bin to float, src/points_io.cpp:63-111; this undoes it on upload), norms, and the norm-sorted,
 // 128-byte-row layout the tensor kernel streams (see topk_tc.cuh).
-#pragma once
 #include "common.cuh"
+#include "params.h"
 
 namespace gpann {
 
@@ -72,7 +72,7 @@ __global__ void gather_sorted_rows_kernel(const unsigned char* rows, size_t n, i
 // Queries for the byte tensor kernel: float [nq,d] -> byte rows [nq_pad,128] + int32 norms; clears *ok when a
 // coordinate is not an integer in the storage's range (the caller then takes the exact float path instead).
 __global__ void prep_queries_bytes_kernel(const float* q, int nq, int d, int nq_pad, int is_signed, unsigned char* out_rows,
-                                          int32_t* out_norms, int* ok) {
+                                          int32_t* out_norms, int* ok, uint32_t* bound) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nq_pad; r += warps) {
@@ -96,9 +96,34 @@ __global__ void prep_queries_bytes_kernel(const float* q, int nq, int d, int nq_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
         reinterpret_cast<uint32_t*>(out_rows + (size_t) r * 128)[lane] = word;
-        if (lane == 0) out_norms[r] = nrm;
+        if (lane == 0) {
+            out_norms[r] = nrm;
+            if (bound) bound[r] = 0x7f800000u;  // +inf: no bound yet
+        }
         if (!__all_sync(0xffffffffu, good) && lane == 0) atomicAnd(ok, 0);
     }
+}
+
+void launch_detect_bytes(const float* x, size_t count, int* flags, int blocks, cudaStream_t st) {
+    detect_bytes_kernel<<<blocks, 256, 0, st>>>(x, count, flags);
+}
+void launch_narrow_rows(const float* x, size_t n, int d, int pitch, unsigned char* out, int blocks, cudaStream_t st) {
+    narrow_rows_kernel<<<blocks, 256, 0, st>>>(x, n, d, pitch, out);
+}
+void launch_byte_norms(const unsigned char* rows, size_t n, int d, size_t pitch, int is_signed, uint32_t* norms, uint32_t* index,
+                       int blocks, cudaStream_t st) {
+    byte_norms_kernel<<<blocks, 256, 0, st>>>(rows, n, d, pitch, is_signed, norms, index);
+}
+void launch_gather_sorted_rows(const unsigned char* rows, size_t n, int d, size_t pitch, const uint32_t* perm,
+                               const uint32_t* sorted_norms, uint32_t id_base, size_t n_pad, unsigned char* out_rows,
+                               int32_t* out_norms, uint32_t* out_ids, int blocks, cudaStream_t st) {
+    gather_sorted_rows_kernel<<<blocks, 256, 0, st>>>(rows, n, d, pitch, perm, sorted_norms, id_base, n_pad, out_rows, out_norms,
+                                                      out_ids);
+}
+void launch_prep_queries_bytes(const float* q, int nq, int d, int nq_pad, int is_signed, unsigned char* out_rows, int32_t* out_norms,
+                               int* ok, uint32_t* bound, cudaStream_t st) {
+    const unsigned blocks = (unsigned) ((((size_t) nq_pad * 32 + 255) / 256) < 1024 ? (((size_t) nq_pad * 32 + 255) / 256) : 1024);
+    prep_queries_bytes_kernel<<<blocks, 256, 0, st>>>(q, nq, d, nq_pad, is_signed, out_rows, out_norms, ok, bound);
 }
 
 }  // namespace gpann

@@ -1,4 +1,4 @@
-// stream.cuh -- HBM-streaming exact scan (CUDA cores) + key merge.
+// stream.cu -- HBM-streaming exact scan (CUDA cores) + key merge.
 //
 // Replaces the reference's scalar triple loop `for query: for point: distance(); TopN.Add()`
 // (src/recall.h:27-37, src/defs.cpp:87-96, src/inverted_index.h:43-75) for SMALL query batches, where the path
@@ -11,91 +11,11 @@
 // that query, appends it to a shared-memory candidate buffer; a warp compacts a buffer (register bitonic
 // select) before it could overflow, which also tightens the threshold.  Each CTA finally emits its k best
 // keys per query and merge_keys_kernel reduces over CTAs.
-#pragma once
 #include "common.cuh"
+#include "distance.cuh"
+#include "params.h"
 
 namespace gpann {
-
-constexpr int kStreamTile = 128;  // points per tile == threads per CTA
-
-struct StreamParams {
-    const char* rows;       // first row of the point set
-    size_t pitch;           // bytes between rows
-    int storage;            // kF32 / kU8 / kS8
-    int d;
-    size_t row_begin, row_end;  // scanned row range
-    const uint32_t* ids;    // optional per-row ids (norm-sorted layouts); else id = id_base + row
-    uint32_t id_base;
-    uint32_t id_lo, id_hi;  // keep only ids in [id_lo, id_hi)
-    const float* queries;   // [nq, d]
-    int nq, k, metric;
-    int qb;                 // queries per batch (blockIdx.y selects the batch)
-    int cap;                // candidate buffer capacity per query (power of two, >= k + kStreamTile)
-    int spitch;             // shared-memory row pitch in bytes (odd multiple of 16)
-    int qpitch;             // shared-memory query pitch in floats (multiple of 4)
-    int vec_ok;             // rows can be fetched with 16-byte loads
-    uint64_t* partial;      // [gridDim.x, nq, k]
-};
-
-template <int STORAGE>
-__device__ __forceinline__ void load8(const char* row, int i, float (&x)[8]) {
-    if constexpr (STORAGE == kF32) {
-        const float4 a = *reinterpret_cast<const float4*>(row + (size_t) i * 4);
-        const float4 b = *reinterpret_cast<const float4*>(row + (size_t) i * 4 + 16);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-    } else {
-        const uint2 w = *reinterpret_cast<const uint2*>(row + i);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t word = j < 4 ? w.x : w.y;
-            const uint32_t byte = (word >> (8 * (j & 3))) & 0xFFu;
-            x[j] = STORAGE == kU8 ? (float) byte : (float) (int) (int8_t) byte;
-        }
-    }
-}
-template <int STORAGE>
-__device__ __forceinline__ float load1(const char* row, int i) {
-    if constexpr (STORAGE == kF32) return reinterpret_cast<const float*>(row)[i];
-    if constexpr (STORAGE == kU8) return (float) reinterpret_cast<const uint8_t*>(row)[i];
-    return (float) reinterpret_cast<const int8_t*>(row)[i];
-}
-
-// Distance of one shared-memory point row to one shared-memory query row, reference arithmetic order.
-template <int STORAGE>
-__device__ __forceinline__ float ref_distance(const char* row, const float* q, int d, int metric) {
-    if (metric == kL2) {
-        float l[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int d16 = d & ~15;
-        for (int i = 0; i < d16; i += 8) {
-            float x[8];
-            load8<STORAGE>(row, i, x);
-            const float4 qa = *reinterpret_cast<const float4*>(q + i);
-            const float4 qb = *reinterpret_cast<const float4*>(q + i + 4);
-            float t;
-            t = x[0] - qa.x; l[0] = __fmaf_rn(t, t, l[0]);
-            t = x[1] - qa.y; l[1] = __fmaf_rn(t, t, l[1]);
-            t = x[2] - qa.z; l[2] = __fmaf_rn(t, t, l[2]);
-            t = x[3] - qa.w; l[3] = __fmaf_rn(t, t, l[3]);
-            t = x[4] - qb.x; l[4] = __fmaf_rn(t, t, l[4]);
-            t = x[5] - qb.y; l[5] = __fmaf_rn(t, t, l[5]);
-            t = x[6] - qb.z; l[6] = __fmaf_rn(t, t, l[6]);
-            t = x[7] - qb.w; l[7] = __fmaf_rn(t, t, l[7]);
-        }
-        float res = __fadd_rn(l[0], l[1]);
-#pragma unroll
-        for (int j = 2; j < 8; ++j) res = __fadd_rn(res, l[j]);
-        float tail = 0.f;
-        for (int i = d16; i < d; ++i) {
-            const float t = load1<STORAGE>(row, i) - q[i];
-            tail = __fmaf_rn(t, t, tail);
-        }
-        return __fadd_rn(res, tail);
-    } else {
-        float r = 0.f;
-        for (int i = 0; i < d; ++i) r = __fmaf_rn(q[i], load1<STORAGE>(row, i), r);
-        return __fsub_rn(1.0f, r);
-    }
-}
 
 template <int STORAGE>
 __global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamParams p) {
@@ -163,7 +83,7 @@ __global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamPa
             const int cnt = s_cnt[q];
             if (cnt > p.cap - kStreamTile) {
                 uint64_t* b = s_buf + (size_t) q * p.cap;
-                const uint64_t kth = warp_select_topk_dyn(b, cnt, p.k, b, lane, p.cap);
+                const uint64_t kth = warp_select_topk_dyn<32>(b, cnt, p.k, b, lane, p.cap);
                 if (lane == 0) {
                     s_cnt[q] = min(cnt, p.k);
                     s_thr[q] = kth;
@@ -176,26 +96,13 @@ __global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamPa
     for (int q = warp; q < nqb; q += kStreamTile / 32) {
         uint64_t* b = s_buf + (size_t) q * p.cap;
         uint64_t* dst = p.partial + ((size_t) blockIdx.x * p.nq + (q0 + q)) * p.k;
-        warp_select_topk_dyn(b, s_cnt[q], p.k, dst, lane, p.cap);
+        warp_select_topk_dyn<32>(b, s_cnt[q], p.k, dst, lane, p.cap);
     }
 }
 
 // Merge `parts` ascending key lists per query into the k smallest.  One warp per query; keys [parts, nq, k].
 // Output: any of out_dist [nq,k] (float), out_id [nq,k], out_keys [nq,k], out_count [nq], out_kth [nq] (the
 // reference's Top().first: the largest kept distance).
-struct MergeParams {
-    const uint64_t* keys;
-    size_t parts, nq;
-    size_t nq_stride;  // queries per part in `keys` (>= nq: padded layouts)
-    int k;
-    int cap;  // power of two >= 2*k' where k' = 32-rounded k; selection window
-    float* out_dist;
-    uint32_t* out_id;
-    uint64_t* out_keys;
-    uint32_t* out_count;
-    float* out_kth;
-};
-
 __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -215,7 +122,7 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
         }
         __syncwarp();
         cnt += take;
-        warp_select_topk_dyn(win, cnt, p.k, win, lane, p.cap);
+        warp_select_topk_dyn<32>(win, cnt, p.k, win, lane, p.cap);
         cnt = min(cnt, p.k);
     }
     __syncwarp();
@@ -232,8 +139,27 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
     if (lane == 0) {
         if (p.out_count) p.out_count[q] = valid;
-        if (p.out_kth) p.out_kth[q] = valid ? key_dist(win[valid - 1]) : __int_as_float(0x7f800000);
+        const bool have = p.kth_full_only ? (valid == (uint32_t) p.k) : (valid > 0);
+        if (p.out_kth) p.out_kth[q] = have ? key_dist(win[valid - 1]) : __int_as_float(0x7f800000);
     }
+}
+
+cudaError_t stream_set_attributes() {
+    const int big = 200 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(topk_stream_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(topk_stream_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(topk_stream_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    return e;
+}
+
+void launch_topk_stream(const StreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    if (p.storage == kF32) topk_stream_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
+    else if (p.storage == kU8) topk_stream_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
+    else topk_stream_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
+}
+
+void launch_merge_keys(const MergeParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+    merge_keys_kernel<<<grid, 128, smem, st>>>(p);
 }
 
 }  // namespace gpann

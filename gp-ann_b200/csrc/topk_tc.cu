@@ -1,0 +1,511 @@
+// topk_tc.cu -- tcgen05 / TMEM / TMA tile kernel: batched byte-vector L2 distances fused with per-query top-k.
+//
+// Replaces the reference's `for query: for point: distance(); TopN.Add()` (src/recall.h:25-39) for uint8 /
+// int8 data (BigANN-style, widened to float by the reference's reader, src/points_io.cpp:63-111).  For
+// integer coordinates every partial sum of src/dist.cpp:9-16 is an exact integer below 2^24, so
+//     dist(q,x) = |q|^2 + |x|^2 - 2 q.x          (all int32)
+// is bit-identical to the reference's float result; q.x is the only O(n*nq*d) term and runs on the tensor
+// cores as u8 x u8 -> s32 (tcgen05.mma.kind::i8).
+//
+// Layout in HBM (built once per point set by prep.cu): point rows are SORTED BY NORM, padded to 128-byte rows
+// and to a multiple of 256 rows; norms[] (int32) and ids[] (original id) ride along.  Because a 256-point
+// tile then holds near-equal norms, the top-k test against the running k-th best distance kth_q
+//     2*acc >= |q|^2 + |x|^2 - kth_q      <=     acc >= ceil((|q|^2 - kth_q + min_tile|x|^2) / 2) =: T
+// needs no per-value norm: the epilogue takes a 3-input max over the accumulators straight out of TMEM
+// (VIMNMX3, half an instruction per distance) and compares once per 32 values.  Values reaching T are rare
+// (k / points-seen): the filter warps turn them into exact (distance,id) keys and push them into a shared-memory
+// queue; dedicated SELECTION warps pop the records, keep every query's exact top-k list (replace-the-maximum for
+// k <= 32, append + warp-wide bitonic compaction above) and publish the tightened threshold back through shared
+// memory.  The tensor pipeline (TMA -> MMA -> TMEM drain) therefore never waits for selection work.
+//
+// CTA roles (384 threads, 1 CTA/SM, persistent over its point range):
+//   warp 0 lane 0 : TMA producer -- Q tiles once, then per point tile 256x128B rows (SWIZZLE_128B) + its 256 norms
+//                                   + 256 ids into a kStages ring, all on one mbarrier
+//   warp 1 lane 0 : MMA issuer   -- per (point tile, Q tile) "item": ceil(d/32) x tcgen05.mma M128 N256 K32 into
+//                                   TMEM accumulator slot (item & 1); tcgen05.commit -> mbarriers
+//   warps 2..9    : filter       -- two groups of 4 warps; group h drains slot h, i.e. the items with parity h
+//                                   (R is even, so item parity == Q-tile parity).  Warp (w & 3) owns TMEM lanes
+//                                   32*(w&3)..: tcgen05.ld 32x32b.x32 x2, max3 tree, one compare per 64 values.
+//   warps 10..11  : selection    -- one candidate queue each; exact top-k lists in global memory (L2), thresholds in smem
+// Grid: G query groups (R Q-tiles of 128 queries, resident in shared memory) x S point splits.
+#include "common.cuh"
+#include "params.h"
+
+namespace gpann {
+namespace tc {
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes and addresses multiples of 16)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((saddr >> 4) & 0x3FFFu);  // start address, 16-byte units
+    d |= (uint64_t) 1 << 16;                   // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t) (1024 >> 4) << 32;         // stride byte offset between 8-row groups
+    d |= (uint64_t) 1 << 46;                   // descriptor version (sm_100)
+    d |= (uint64_t) 2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }  // -> VIMNMX3
+// max of 32 accumulators as a depth-4 tree of 3-input maxima (16 independent-ish VIMNMX3 instead of a chain)
+__device__ __forceinline__ int max32(const uint32_t (&v)[32]) {
+    int a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = max3((int) v[3 * i], (int) v[3 * i + 1], (int) v[3 * i + 2]);
+    a[10] = max((int) v[30], (int) v[31]);
+    const int b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
+    return max(max3(b0, b1, b2), b3);
+}
+
+// ---- candidate queues: epilogue lanes push (key, query slot) records, a selection warp pops them ------------------
+// Single consumer per queue; a slot's qs word doubles as its ready flag (kQEmpty = free).
+constexpr uint32_t kQEmpty = 0xFFFFFFFFu;
+
+struct Queue {
+    uint64_t* key;            // [kQueueCap]
+    volatile uint32_t* qs;    // [kQueueCap]
+    uint32_t* tail;           // reserved by producers (atomicAdd)
+    volatile uint32_t* head;  // consumed (written by the consumer's lane 0)
+};
+
+__device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs) {
+    const uint32_t pos = atomicAdd(q.tail, 1u);
+    if (pos - *q.head >= (uint32_t) kQueueCap) {  // full: wait for the selection warp (rare)
+        const uint64_t t0 = global_timer_ns();
+        while (pos - *q.head >= (uint32_t) kQueueCap) {
+            __nanosleep(64);
+            if (global_timer_ns() - t0 > 4000000000ull) __trap();
+        }
+    }
+    const uint32_t slot = pos & (kQueueCap - 1);
+    q.key[slot] = key;
+    __threadfence_block();
+    q.qs[slot] = qs;
+}
+
+// Exact re-test of the values of one 32-column chunk that reached the filter threshold: compute the integer
+// distance, build the (distance,id) key and hand it to the selection warp that owns the query.
+__device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, const int32_t* tn, const uint32_t* ti, int col0,
+                                              int nqv, uint32_t qs, const Queue& q) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int acc = (int) v[j];
+        if (acc >= T) {
+            const uint32_t id = ti[col0 + j];
+            if (id != kInvalidId) {
+                const int dist = nqv + tn[col0 + j] - 2 * acc;
+                queue_push(q, pack_key((float) dist, id), qs);
+            }
+        }
+    }
+}
+
+// Per-query selection state owned by the selection warps (shared memory, indexed by query slot qs).
+struct SelState {
+    uint64_t* kth;   // current k-th best key (kEmptyKey until k keys are held)
+    int* U;          // |q|^2 - kth distance: what the epilogue turns into its filter threshold
+    int* cnt;        // keys held in the query's list
+    int* maxpos;     // position of the k-th best (largest kept) key in the unsorted list (k <= 32)
+    const int* nq;   // |q|^2
+    uint64_t* lists; // global: [nslots][cap] keys of this CTA
+    int k, cap;
+};
+
+// Insert one record.  k <= 32: unsorted list of the k best with replace-the-maximum (exact threshold after every
+// insert).  Larger k: append; the caller compacts a full list warp-wide.  Returns true if the list needs compaction.
+__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key) {
+    uint64_t* list = s.lists + (size_t) qs * s.cap;
+    int cnt = s.cnt[qs];
+    if (s.k <= 32) {
+        if (cnt < s.k) {
+            list[cnt++] = key;
+            s.cnt[qs] = cnt;
+            if (cnt < s.k) return false;
+        } else {
+            if (key >= s.kth[qs]) return false;
+            list[s.maxpos[qs]] = key;
+        }
+        uint64_t m = 0;
+        int mp = 0;
+        for (int i = 0; i < s.k; ++i) {
+            const uint64_t x = __ldcg(list + i);
+            if (x >= m) {
+                m = x;
+                mp = i;
+            }
+        }
+        s.kth[qs] = m;
+        s.maxpos[qs] = mp;
+        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) key_dist(m));
+        return false;
+    }
+    if (key >= s.kth[qs]) return false;
+    list[cnt++] = key;
+    s.cnt[qs] = cnt;
+    return cnt >= s.cap;
+}
+
+__device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane) {
+    uint32_t head = 0;
+    while (true) {
+        const uint32_t finished = *done;  // read BEFORE the tail: once all producers are done the tail is final
+        __threadfence_block();
+        const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(q.tail);
+        const uint32_t avail = tail - head;
+        if (avail == 0) {
+            if (finished == (uint32_t) kEpiWarps) break;
+            __nanosleep(200);
+            continue;
+        }
+        const uint32_t n = min(avail, 32u);
+        uint32_t qs = 0xFFFF0000u + lane;  // unique dummy for idle lanes (never matches a real slot)
+        uint64_t key = 0;
+        bool pending = (uint32_t) lane < n;
+        if (pending) {
+            const uint32_t slot = (head + lane) & (kQueueCap - 1);
+            uint32_t w = q.qs[slot];
+            if (w == kQEmpty) {
+                const uint64_t t0 = global_timer_ns();
+                while ((w = q.qs[slot]) == kQEmpty) {
+                    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+                }
+            }
+            __threadfence_block();
+            key = q.key[slot];
+            qs = w;
+            q.qs[slot] = kQEmpty;
+        }
+        __threadfence_block();
+        __syncwarp();
+        head += n;
+        if (lane == 0) *q.head = head;  // slots reusable
+        // records for the same query are applied one per round (lowest lane first)
+        while (__any_sync(0xffffffffu, pending)) {
+            const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
+            bool compact = false;
+            if (pending && (__ffs(peers) - 1) == lane) {
+                compact = select_insert(s, qs, key);
+                pending = false;
+            }
+            __syncwarp();
+            unsigned need = __ballot_sync(0xffffffffu, compact);
+            while (need) {  // k > 32 only: a full list is compacted by the whole warp
+                const int L = __ffs(need) - 1;
+                need &= need - 1;
+                const uint32_t qsL = __shfl_sync(0xffffffffu, qs, L);
+                uint64_t* b = s.lists + (size_t) qsL * s.cap;
+                const uint64_t newkth = warp_select_topk_dyn<16>(b, s.cap, s.k, b, lane, s.cap);
+                if (lane == L) {
+                    s.cnt[qsL] = s.k;
+                    s.kth[qsL] = newkth;
+                    s.U[qsL] = max(s.U[qsL], s.nq[qsL] - (int) key_dist(newkth));
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q, const Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = a.R;
+    const int g = blockIdx.x % a.G, s = blockIdx.x / a.G;
+    // logical tile indices [tile_begin, tile_end) of this split; physical tile = tile_lo + index * tile_stride
+    const uint32_t tile_begin = (uint32_t) (((uint64_t) a.ntiles * s) / a.S);
+    const uint32_t tile_end = (uint32_t) (((uint64_t) a.ntiles * (s + 1)) / a.S);
+
+    // ---- carve shared memory (operand tiles 1024-byte aligned for SWIZZLE_128B) ----
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+    unsigned char* base = smem_raw + pad;
+    const uint32_t sQ = raw_addr + pad;
+    const uint32_t sP = sQ + R * kQTileBytes;
+    unsigned char* after = base + (size_t) R * kQTileBytes + (size_t) kStages * kPTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(after);  // full[kStages], empty[kStages], qfull, tfull[2], tempty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages, bar_q = bar_empty + 8 * kStages,
+                   bar_tfull = bar_q + 8, bar_tempty = bar_tfull + 16;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 8 * (2 * kStages + 5));
+    uint32_t* s_ctr = reinterpret_cast<uint32_t*>(after + 128);               // q_tail[2], q_head[2], done
+    int32_t* s_norm = reinterpret_cast<int32_t*>(after + 256);                 // [kStages][256]
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_norm + kStages * kTileN);   // [kStages][256]
+    uint64_t* s_kth = reinterpret_cast<uint64_t*>(s_id + kStages * kTileN);    // [R*128]
+    uint64_t* s_qkey = s_kth + R * kTileM;                                     // [kSelWarps][kQueueCap]
+    uint32_t* s_qqs = reinterpret_cast<uint32_t*>(s_qkey + kSelWarps * kQueueCap);  // [kSelWarps][kQueueCap]
+    int* s_U = reinterpret_cast<int*>(s_qqs + kSelWarps * kQueueCap);          // [R*128]
+    int* s_cnt = s_U + R * kTileM;
+    int* s_nq = s_cnt + R * kTileM;
+    int* s_maxpos = s_nq + R * kTileM;
+
+    const int nslots = R * kTileM;
+    const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
+    for (int i = tid; i < nslots; i += kThreads) {
+        const int nqv = a.qnorm[qbase + i];
+        s_kth[i] = kEmptyKey;
+        s_cnt[i] = 0;
+        s_maxpos[i] = 0;
+        s_nq[i] = nqv;
+        // warm start: an upper bound on this query's kth distance from the sample pre-pass (+inf = none)
+        const float b = a.bound ? __uint_as_float(a.bound[qbase + i]) : __int_as_float(0x7f800000);
+        s_U[i] = (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
+    }
+    for (int i = tid; i < kSelWarps * kQueueCap; i += kThreads) s_qqs[i] = kQEmpty;
+    if (tid < 8) s_ctr[tid] = 0;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_p);
+        prefetch_tmap(&tmap_q);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1 + kEpiWarps);  // MMA commit + every epilogue warp done with the tile
+        }
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, kEpiWarps / 2);  // one arrive per warp of the slot's epilogue group
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"((uint32_t) kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    uint64_t* my_lists = a.cand + (size_t) blockIdx.x * nslots * a.cap;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(bar_q, (uint32_t) (R * kQTileBytes));
+            for (int r = 0; r < R; ++r) tma_load_2d(sQ + r * kQTileBytes, &tmap_q, bar_q, 0, (int) ((g * R + r) * kTileM));
+            for (uint32_t t = tile_begin; t < tile_end; ++t) {
+                const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+                mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                mbar_expect_tx(bar_full + 8 * st, kPTileBytes + 2 * kTileN * 4);
+                const size_t row0 = ((size_t) a.tile_lo + (size_t) t * a.tile_stride) * kTileN;
+                tma_load_2d(sP + st * kPTileBytes, &tmap_p, bar_full + 8 * st, 0, (int) row0);
+                bulk_load_1d(smem_u32(s_norm + st * kTileN), a.pnorm + row0, kTileN * 4, bar_full + 8 * st);
+                bulk_load_1d(smem_u32(s_id + st * kTileN), a.pid + row0, kTileN * 4, bar_full + 8 * st);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            mbar_wait(bar_q, 0);
+            tcgen05_fence_after();
+            uint32_t it = 0;
+            for (uint32_t t = tile_begin; t < tile_end; ++t) {
+                const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+                mbar_wait(bar_full + 8 * st, ph);
+                tcgen05_fence_after();
+                const uint64_t bdesc = make_sw128_desc(sP + st * kPTileBytes);
+                for (int r = 0; r < R; ++r, ++it) {
+                    const uint32_t slot = it & 1, sph = (it >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * slot, sph ^ 1);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_sw128_desc(sQ + r * kQTileBytes);
+                    const uint32_t dcol = tmem_base + slot * kTileN;
+                    for (int ks = 0; ks < a.nks; ++ks)  // +32 bytes of K per step = +2 in 16-byte units
+                        umma_i8(dcol, adesc + 2 * ks, bdesc + 2 * ks, a.idesc, ks > 0 ? 1u : 0u);
+                    umma_commit(bar_tfull + 8 * slot);  // accumulator ready for the epilogue
+                }
+                umma_commit(bar_empty + 8 * st);  // operands consumed (1 of 1+kEpiWarps arrivals)
+            }
+        }
+    } else if (warp < 2 + kEpiWarps) {
+        // ===== epilogue (filter): group h = slot h = Q tiles of parity h; warp (w & 3) owns TMEM lanes [32*(w&3), +32) =====
+        const int ew = warp - 2;
+        const int h = ew >> 2;
+        const int wq = warp & 3;
+        const int qrow = wq * 32 + lane;
+        const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
+        uint32_t n_mine = 0;  // items this group has drained from its slot
+        for (uint32_t t = tile_begin; t < tile_end; ++t) {
+            const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+            // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
+            mbar_wait(bar_full + 8 * st, ph);
+            const int32_t* tn = s_norm + st * kTileN;
+            const uint32_t* ti = s_id + st * kTileN;
+            const int nmin = tn[0];
+            for (int r = h; r < R; r += 2, ++n_mine) {
+                const uint32_t sph = n_mine & 1;
+                const uint32_t qs = (uint32_t) (r * kTileM + qrow);
+                const int T = (*reinterpret_cast<volatile int*>(s_U + qs) + nmin + 1) >> 1;
+                const int nqv = s_nq[qs];
+                const int sel = (int) (qs >> 5) & (kSelWarps - 1);
+                Queue q;
+                q.key = s_qkey + sel * kQueueCap;
+                q.qs = s_qqs + sel * kQueueCap;
+                q.tail = s_ctr + sel;
+                q.head = s_ctr + kSelWarps + sel;
+                mbar_wait(bar_tfull + 8 * h, sph);
+                tcgen05_fence_after();
+                const uint32_t tbase = tmem_base + h * kTileN + lane_sel;
+                if (a.mode != 2) {
+#pragma unroll 1
+                    for (int c = 0; c < kTileN / 64; ++c) {
+                        uint32_t va[32], vb[32];
+                        tmem_ld32(tbase + c * 64, va);
+                        tmem_ld32(tbase + c * 64 + 32, vb);
+                        tmem_wait_ld();
+                        const int ma = max32(va), mb = max32(vb);
+                        if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
+                            if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
+                            continue;
+                        }
+                        if (__any_sync(0xffffffffu, max(ma, mb) >= T)) {
+                            if (ma >= T) enqueue_chunk(va, T, tn, ti, c * 64, nqv, qs, q);
+                            if (mb >= T) enqueue_chunk(vb, T, tn, ti, c * 64 + 32, nqv, qs, q);
+                            __syncwarp();
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms/ids
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(s_ctr + 2 * kSelWarps, 1u);  // done: every record of this warp is in a queue
+    } else {
+        // ===== selection warps: exact per-query top-k lists, thresholds published through s_U =====
+        const int sel = warp - (2 + kEpiWarps);
+        Queue q;
+        q.key = s_qkey + sel * kQueueCap;
+        q.qs = s_qqs + sel * kQueueCap;
+        q.tail = s_ctr + sel;
+        q.head = s_ctr + kSelWarps + sel;
+        SelState ss;
+        ss.kth = s_kth;
+        ss.U = s_U;
+        ss.cnt = s_cnt;
+        ss.maxpos = s_maxpos;
+        ss.nq = s_nq;
+        ss.lists = my_lists;
+        ss.k = a.k;
+        ss.cap = a.cap;
+        selection_warp_loop(q, ss, s_ctr + 2 * kSelWarps, lane);
+    }
+
+    // ---- final selection: every query's k best of this CTA's point range -> partial[s], by all non-role warps ----
+    if (warp >= 2) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + kSelWarps)) : "memory");
+        for (int qs = warp - 2; qs < nslots; qs += kEpiWarps + kSelWarps) {
+            const uint64_t* b = my_lists + (size_t) qs * a.cap;
+            uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
+            const int cnt = s_cnt[qs];
+            warp_select_topk_dyn<16>(b, cnt, a.k, dst, lane, min(a.cap, max(32, pow2_ceil(max(cnt, a.k)))));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols)
+                     : "memory");
+    }
+}
+
+}  // namespace tc
+
+cudaError_t tc_set_attributes() {
+    return cudaFuncSetAttribute(tc::topk_tc_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) tc::smem_bytes(tc::kMaxR));
+}
+
+void launch_topk_tc_bytes(const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid, size_t smem,
+                          cudaStream_t st) {
+    tc::topk_tc_bytes_kernel<<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+}
+
+}  // namespace gpann

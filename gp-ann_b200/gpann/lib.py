@@ -22,6 +22,8 @@ SYMBOLS = {
     "gpann_set_algo": (_i, [_vp, _i]),
     "gpann_launch_count": (_u64, [_vp]),
     "gpann_last_algo": (C.c_char_p, [_vp]),
+    "gpann_set_timing": (_i, [_vp, _i]),
+    "gpann_last_kernel_ms": (C.c_float, [_vp]),
     "gpann_points_upload": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
     "gpann_points_upload_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
     "gpann_points_from_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, C.POINTER(_vp)]),
@@ -127,6 +129,13 @@ class Context:
     @property
     def last_algo(self):
         return self.lib.gpann_last_algo(self.h).decode()
+
+    def set_timing(self, on):
+        self.check(self.lib.gpann_set_timing(self.h, int(on)))
+
+    def last_kernel_ms(self):
+        """Duration of the last bracketed dominant kernel (waits for it); needs set_timing(True)."""
+        return float(self.lib.gpann_last_kernel_ms(self.h))
 
     @property
     def launch_count(self):

@@ -12,7 +12,8 @@
  *  - Every function returns 0 on success or a negative GPANN_E_* code; gpann_last_error(ctx) has the text.
  *  - Host entry points borrow caller-owned host buffers for the duration of the call; the library owns all
  *    device memory behind the opaque handles.  The *_device entry points take device pointers and a
- *    cudaStream_t (as void*) and are asynchronous on that stream.
+ *    cudaStream_t (as void*) and are asynchronous on that stream; the handle is used verbatim, so NULL is
+ *    the legacy default stream (what torch.cuda.current_stream().cuda_stream reports by default).
  *  - There is NO CPU fallback: without a usable CUDA device gpann_init fails with GPANN_E_CUDA.
  *  - Results are "keys": a (distance, id) pair packed into 64 bits whose unsigned order is the reference's
  *    std::pair<float,uint32_t> lexicographic order (src/topn.h:12-19): ties on distance keep the smaller id.
@@ -56,6 +57,11 @@ int gpann_set_algo(gpann_ctx* ctx, int algo);
 uint64_t gpann_launch_count(const gpann_ctx* ctx);
 /* Name of the kernel family the last gpann_topk* call used ("stream", "tensor_u8", ...). */
 const char* gpann_last_algo(const gpann_ctx* ctx);
+/* Measurement hook: when on, the dominant kernel of each gpann_topk* call (the tcgen05 tile kernel or the
+ * streaming scan) is bracketed by CUDA events on the launching stream; gpann_last_kernel_ms waits for the
+ * last bracket and returns its duration in milliseconds (negative if none was recorded). */
+int gpann_set_timing(gpann_ctx* ctx, int on);
+float gpann_last_kernel_ms(gpann_ctx* ctx);
 
 /* ---- point sets: replaces PointSet (src/defs.h:10-21) as the scanned operand --------------------------- */
 /* Upload n rows of d floats (row-major, as PointSet::coordinates).  Ids reported by gpann_topk are
