@@ -51,7 +51,21 @@ def build(force=False, verbose=False):
     objs = [o for o, _ in results]
     if force or any(changed for _, changed in results) or not os.path.exists(OUT):
         subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
+    build_dropin(force)
     return OUT
+
+
+def build_dropin(force=False):
+    """libgpann_dropin.so: the C++ drop-in layer (cxx/: reference-shaped dist.h/topn.h/recall.h/kmeans.h over the C
+    ABI) behind a small C shim, so the tests can drive it.  Plain g++, links libgpann_cuda.so via $ORIGIN."""
+    cxx = os.path.join(HERE, "cxx")
+    out = os.path.join(HERE, "libgpann_dropin.so")
+    srcs = [os.path.join(cxx, f) for f in ("dropin_shim.cpp", "dist.cpp", "kmeans_gpu.cpp")]
+    deps = srcs + [os.path.join(cxx, f) for f in os.listdir(cxx)] + [OUT]
+    if force or _stale(out, deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-o", out, *srcs,
+                               "-L" + HERE, "-lgpann_cuda", "-Wl,-rpath,$ORIGIN"])
+    return out
 
 
 if __name__ == "__main__":

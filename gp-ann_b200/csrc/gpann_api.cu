@@ -278,8 +278,7 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
     *queries_ok_host = 1;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
         const size_t nqb = std::min(batch_max, nq - q0);
-        // R (Q tiles resident per CTA) is 2 or 4: even, so that each query is owned by one epilogue thread
-        const int R = nqb > 2 * (size_t) tc::kTileM ? 4 : 2;
+        const int R = (int) std::min<size_t>(tc::kMaxR, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
         const int G = (int) ((nqb + (size_t) R * tc::kTileM - 1) / ((size_t) R * tc::kTileM));
         const uint32_t tiles_total = (uint32_t) (pts->n_pad / tc::kTileN);
         const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / G), tiles_total));
@@ -322,19 +321,25 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
         a.mode = ctx->tc_mode;
         const unsigned grid = (unsigned) (G * S);
         const size_t smem = tc::smem_bytes(R);
-        // Pre-pass over a strided sample of tiles: its k-th distances are valid upper bounds on the final ones and
-        // let every CTA of the main pass start with a tight filter threshold instead of a cold one.
-        const uint32_t sample_per_split = 12;
-        if (ctx->tc_prepass && ctx->tc_mode == 0 && tiles_total >= 64u * (uint32_t) S * sample_per_split) {
-            a.ntiles = (uint32_t) S * sample_per_split;
-            a.tile_stride = tiles_total / a.ntiles;
-            a.tile_lo = a.tile_stride / 2;
-            launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
-            GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel(sample)"));
-            TopkOut b;
-            b.kth = (float*) ctx->bound.p;  // float bits: read back by the kernel as the bound
-            b.kth_full_only = 1;
-            GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, b, 0, st));
+        // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
+        // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
+        // (a cold start pushes EVERY distance through the selection warps).  Two levels: 1 tile per split (cold, but
+        // tiny), then 12 tiles per split filtered by the level-1 bound.
+        if (ctx->tc_prepass && ctx->tc_mode == 0) {
+            const uint32_t levels[2] = { 1, 12 };
+            for (uint32_t per_split : levels) {
+                const uint32_t nsample = (uint32_t) S * per_split;
+                if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
+                a.ntiles = nsample;
+                a.tile_stride = tiles_total / nsample;
+                a.tile_lo = a.tile_stride / 2;
+                launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
+                GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel(sample)"));
+                TopkOut b;
+                b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
+                b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
+                GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, b, 0, st));
+            }
         }
         a.tile_lo = 0;
         a.tile_stride = 1;

@@ -41,7 +41,7 @@ struct MergeParams {
     uint64_t* out_keys;
     uint32_t* out_count;
     float* out_kth;
-    int kth_full_only;      // out_kth = +inf unless k valid keys were found (a bound must come from a full list)
+    int kth_full_only;      // bound mode: out_kth = min(out_kth, k-th distance) and only if k valid keys were found
 };
 
 // ---- kmeans.cu ----------------------------------------------------------------------------------------------
@@ -99,7 +99,7 @@ struct Args {
     const int32_t* pnorm;    // [n_pad] ascending
     const uint32_t* pid;     // [n_pad] original ids, kInvalidId on padding rows
     const int32_t* qnorm;    // [G*R*128]
-    int R, G, S;             // Q tiles per CTA (2 or 4), query groups, point splits
+    int R, G, S;             // Q tiles per CTA (1..4), query groups, point splits
     int nks;                 // K steps of 32 bytes
     int k, cap;              // top-k and candidate buffer capacity (power of two >= k + 64)
     uint32_t tile_lo, tile_stride, ntiles;  // this launch scans tiles tile_lo + i*tile_stride, i in [0,ntiles)

@@ -140,7 +140,11 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
     if (lane == 0) {
         if (p.out_count) p.out_count[q] = valid;
         const bool have = p.kth_full_only ? (valid == (uint32_t) p.k) : (valid > 0);
-        if (p.out_kth) p.out_kth[q] = have ? key_dist(win[valid - 1]) : __int_as_float(0x7f800000);
+        if (p.out_kth) {
+            float v = have ? key_dist(win[valid - 1]) : __int_as_float(0x7f800000);
+            if (p.kth_full_only) v = fminf(v, p.out_kth[q]);  // bounds only ever tighten
+            p.out_kth[q] = v;
+        }
     }
 }
 

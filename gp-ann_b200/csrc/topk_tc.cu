@@ -23,9 +23,9 @@
 //                                   + 256 ids into a kStages ring, all on one mbarrier
 //   warp 1 lane 0 : MMA issuer   -- per (point tile, Q tile) "item": ceil(d/32) x tcgen05.mma M128 N256 K32 into
 //                                   TMEM accumulator slot (item & 1); tcgen05.commit -> mbarriers
-//   warps 2..9    : filter       -- two groups of 4 warps; group h drains slot h, i.e. the items with parity h
-//                                   (R is even, so item parity == Q-tile parity).  Warp (w & 3) owns TMEM lanes
-//                                   32*(w&3)..: tcgen05.ld 32x32b.x32 x2, max3 tree, one compare per 64 values.
+//   warps 2..9    : filter       -- all 8 warps drain every item: warp (w & 3) owns TMEM lanes 32*(w&3).. and the
+//                                   column half (w-2)/4 (128 columns): tcgen05.ld 32x32b.x32 x2, max3 tree, one
+//                                   compare per 64 values.  They hold no per-query state (read-only thresholds).
 //   warps 10..11  : selection    -- one candidate queue each; exact top-k lists in global memory (L2), thresholds in smem
 // Grid: G query groups (R Q-tiles of 128 queries, resident in shared memory) x S point splits.
 #include "common.cuh"
@@ -343,7 +343,7 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, kEpiWarps / 2);  // one arrive per warp of the slot's epilogue group
+            mbar_init(bar_tempty + 8 * i, kEpiWarps);  // one arrive per filter warp
         }
         fence_barrier_init();
     }
@@ -399,13 +399,15 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
             }
         }
     } else if (warp < 2 + kEpiWarps) {
-        // ===== epilogue (filter): group h = slot h = Q tiles of parity h; warp (w & 3) owns TMEM lanes [32*(w&3), +32) =====
+        // ===== epilogue (filter): every warp drains every item; warp (w & 3) owns TMEM lanes [32*(w&3), +32) and the
+        // column half (w-2)/4 of the 256-column accumulator =====
         const int ew = warp - 2;
-        const int h = ew >> 2;
+        const int half = ew >> 2;
         const int wq = warp & 3;
         const int qrow = wq * 32 + lane;
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
-        uint32_t n_mine = 0;  // items this group has drained from its slot
+        const int col_base = half * (kTileN / 2);
+        uint32_t it = 0;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
             const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
@@ -413,8 +415,8 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
             const int32_t* tn = s_norm + st * kTileN;
             const uint32_t* ti = s_id + st * kTileN;
             const int nmin = tn[0];
-            for (int r = h; r < R; r += 2, ++n_mine) {
-                const uint32_t sph = n_mine & 1;
+            for (int r = 0; r < R; ++r, ++it) {
+                const uint32_t slot = it & 1, sph = (it >> 1) & 1;
                 const uint32_t qs = (uint32_t) (r * kTileM + qrow);
                 const int T = (*reinterpret_cast<volatile int*>(s_U + qs) + nmin + 1) >> 1;
                 const int nqv = s_nq[qs];
@@ -424,31 +426,37 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                 q.qs = s_qqs + sel * kQueueCap;
                 q.tail = s_ctr + sel;
                 q.head = s_ctr + kSelWarps + sel;
-                mbar_wait(bar_tfull + 8 * h, sph);
+                mbar_wait(bar_tfull + 8 * slot, sph);
                 tcgen05_fence_after();
-                const uint32_t tbase = tmem_base + h * kTileN + lane_sel;
-                if (a.mode != 2) {
+                const uint32_t tbase = tmem_base + slot * kTileN + col_base + lane_sel;
+                if (a.mode == 2) {  // probe: MMA issue rate only
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+                    continue;
+                }
+                // 128 columns per warp and item, 64 at a time.  (Draining all 128 first and releasing the slot early
+                // was measured slower: the drain is bound by the TMEM read path, 128 KB per item ~ 256 B/clk/SM.)
 #pragma unroll 1
-                    for (int c = 0; c < kTileN / 64; ++c) {
-                        uint32_t va[32], vb[32];
-                        tmem_ld32(tbase + c * 64, va);
-                        tmem_ld32(tbase + c * 64 + 32, vb);
-                        tmem_wait_ld();
-                        const int ma = max32(va), mb = max32(vb);
-                        if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
-                            if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
-                            continue;
-                        }
-                        if (__any_sync(0xffffffffu, max(ma, mb) >= T)) {
-                            if (ma >= T) enqueue_chunk(va, T, tn, ti, c * 64, nqv, qs, q);
-                            if (mb >= T) enqueue_chunk(vb, T, tn, ti, c * 64 + 32, nqv, qs, q);
-                            __syncwarp();
-                        }
+                for (int c = 0; c < kTileN / 128; ++c) {
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(tbase + c * 64, va);
+                    tmem_ld32(tbase + c * 64 + 32, vb);
+                    tmem_wait_ld();
+                    const int ma = max32(va), mb = max32(vb);
+                    if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
+                        if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
+                        continue;
+                    }
+                    if (__any_sync(0xffffffffu, max(ma, mb) >= T)) {
+                        if (ma >= T) enqueue_chunk(va, T, tn, ti, col_base + c * 64, nqv, qs, q);
+                        if (mb >= T) enqueue_chunk(vb, T, tn, ti, col_base + c * 64 + 32, nqv, qs, q);
+                        __syncwarp();
                     }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms/ids

@@ -1,0 +1,58 @@
+// gpann_dropin.h -- glue between the reference-shaped C++ entry points (recall.h, kmeans.h, ClosestLeaders) and
+// the C ABI of libgpann_cuda.so (include/gpann.h).
+//
+// One process-wide gpann_ctx on device $GPANN_DEVICE (default 0), created on first use.  The reference calls
+// KMeans concurrently from parlay workers (kmeans_tree_router.cpp:22-37, partitioning.cpp:468-476) while a
+// gpann_ctx is externally synchronised, so every batched call holds the context mutex.  Errors become
+// std::runtime_error, the reference's own convention (kmeans.cpp:229-231); there is no CPU fallback.
+#pragma once
+
+#include <cstdlib>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/gpann.h"
+
+namespace gpann_dropin {
+
+#ifdef MIPS_DISTANCE
+constexpr int kMetric = GPANN_METRIC_MIPS;
+#else
+constexpr int kMetric = GPANN_METRIC_L2;
+#endif
+
+struct Session {
+    gpann_ctx* ctx = nullptr;
+    std::mutex mutex;
+    Session() {
+        const char* dev = std::getenv("GPANN_DEVICE");
+        const int rc = gpann_init(&ctx, dev ? std::atoi(dev) : 0);
+        if (rc != 0)
+            throw std::runtime_error("gpann: no usable CUDA device (gpann_init returned " + std::to_string(rc) +
+                                     "); the GPU hot path has no CPU fallback");
+    }
+    ~Session() { gpann_destroy(ctx); }
+    void check(int rc) const {
+        if (rc != 0) throw std::runtime_error(std::string("gpann: ") + gpann_last_error(ctx));
+    }
+};
+
+inline Session& session() {
+    static Session s;
+    return s;
+}
+
+// RAII upload of a PointSet-like (coordinates/n/d) object.
+template <class PS>
+struct DevicePoints {
+    gpann_points* h = nullptr;
+    DevicePoints(Session& s, PS& ps, int storage = GPANN_STORAGE_AUTO) {
+        s.check(gpann_points_upload(s.ctx, ps.coordinates.data(), ps.n, ps.d, storage, 0, &h));
+    }
+    ~DevicePoints() { gpann_points_free(h); }
+    DevicePoints(const DevicePoints&) = delete;
+    DevicePoints& operator=(const DevicePoints&) = delete;
+};
+
+}  // namespace gpann_dropin
