@@ -43,7 +43,7 @@ struct gpann_ctx {
     bool timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // grow-only scratch, reused across calls (a ctx is externally synchronised)
-    DevBuf partial, cand, qrows, qnorm, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
+    DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
         sort_d, segsums, cent, sums, counts, assign;
 };
 
@@ -63,6 +63,10 @@ struct gpann_points {
     size_t n_pad = 0;
     CUtensorMap tmap;
     bool has_tensor = false;
+    // float storage, d <= 128: norm-sorted bf16 rows [n_pad, dp] + fp32 norms + ids, built lazily by the first
+    // tensor-path query (t_rows / t_norms / t_ids / tmap above are reused for it)
+    int dp = 0;               // padded row length in elements (multiple of 64)
+    bool tensor_tried = false;
 };
 
 namespace {
@@ -126,12 +130,15 @@ int blocks_for(gpann_ctx* ctx, size_t items, int per_block = 256, int waves = 16
     return (int) std::max<size_t>(1, std::min<size_t>((items + per_block - 1) / per_block, (size_t) ctx->num_sms * waves));
 }
 
-int encode_rows_map(gpann_ctx* ctx, CUtensorMap* map, void* base, size_t rows, int box_rows, const char* what) {
-    const cuuint64_t gdim[2] = { (cuuint64_t) tc::kRowBytes, (cuuint64_t) rows };
-    const cuuint64_t gstride[1] = { (cuuint64_t) tc::kRowBytes };
-    const cuuint32_t box[2] = { (cuuint32_t) tc::kRowBytes, (cuuint32_t) box_rows };
+// Row-major [rows, row_elems] operand matrix, fetched as boxes of box_rows x one 128-byte K block, SWIZZLE_128B.
+int encode_rows_map(gpann_ctx* ctx, CUtensorMap* map, void* base, size_t rows, int box_rows, const char* what,
+                    bool bf16 = false, int row_elems = tc::kRowBytes) {
+    const int esz = bf16 ? 2 : 1;
+    const cuuint64_t gdim[2] = { (cuuint64_t) row_elems, (cuuint64_t) rows };
+    const cuuint64_t gstride[1] = { (cuuint64_t) row_elems * esz };
+    const cuuint32_t box[2] = { (cuuint32_t) (tc::kRowBytes / esz), (cuuint32_t) box_rows };
     const cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+    CUresult r = ctx->encode_tiled(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -183,6 +190,52 @@ int build_tensor_bytes(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
     cleanup();
     pts->n_pad = n_pad;
     GP_TRY(encode_rows_map(ctx, &pts->tmap, pts->t_rows, n_pad, tc::kTileN, "points"));
+    pts->has_tensor = true;
+    return 0;
+}
+
+// Lazily built on the first tensor-path query over a float point set (d <= 128): norm-sorted bf16 rows.
+int build_tensor_float(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
+    pts->tensor_tried = true;
+    const size_t n = pts->n;
+    const int d = (int) pts->d;
+    if (n == 0 || d > 64 * tc::kMaxKBlocks || n > 0x7FFFFF00ull || !ctx->encode_tiled) return 0;
+    const int dp = ((d + 63) / 64) * 64;
+    const size_t n_pad = ((n + tc::kTileN - 1) / tc::kTileN) * tc::kTileN;
+    uint32_t *norms = nullptr, *index = nullptr, *norms_sorted = nullptr, *perm = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    auto cleanup = [&]() {
+        cudaFree(norms); cudaFree(index); cudaFree(norms_sorted); cudaFree(perm); cudaFree(tmp);
+    };
+    if (cudaMalloc(&norms, n * 4) != cudaSuccess || cudaMalloc(&index, n * 4) != cudaSuccess ||
+        cudaMalloc(&norms_sorted, n * 4) != cudaSuccess || cudaMalloc(&perm, n * 4) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_float: out of device memory");
+    }
+    launch_float_norms((const float*) pts->rows, n, d, norms, index, blocks_for(ctx, n), st);
+    GP_TRY(check_launch(ctx, "float_norms_kernel"));
+    sort_pairs_u32(nullptr, tmp_bytes, norms, norms_sorted, index, perm, n, 32, st);
+    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess ||
+        sort_pairs_u32(tmp, tmp_bytes, norms, norms_sorted, index, perm, n, 32, st) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_float: radix sort failed");
+    }
+    ctx->launches += 5;
+    if (cudaMalloc(&pts->t_rows, n_pad * (size_t) dp * 2) != cudaSuccess || cudaMalloc(&pts->t_norms, n_pad * 4) != cudaSuccess ||
+        cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_float: out of device memory (layout)");
+    }
+    launch_gather_sorted_rows_bf16((const float*) pts->rows, n, d, dp, perm, norms_sorted, pts->id_base, n_pad,
+                                   (unsigned short*) pts->t_rows, (float*) pts->t_norms, pts->t_ids,
+                                   blocks_for(ctx, n_pad * 32, 256, 32), st);
+    GP_TRY(check_launch(ctx, "gather_sorted_rows_bf16_kernel"));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    cleanup();
+    pts->n_pad = n_pad;
+    pts->dp = dp;
+    GP_TRY(encode_rows_map(ctx, &pts->tmap, pts->t_rows, n_pad, tc::kTileN, "float points", true, dp));
     pts->has_tensor = true;
     return 0;
 }
@@ -268,59 +321,83 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     return launch_merge(ctx, p.partial, gx, nq, nq, k, out, 0, st);
 }
 
-// The tcgen05 path for byte storage.  *queries_ok_host = 0 (and nothing written) when the queries are not
-// integer-valued in the storage's range; the caller then takes the exact float scan.
-int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
-                      cudaStream_t st, int* queries_ok_host) {
+// The tcgen05 path: byte storage (exact int32 distances) or float storage (bf16 filter + exact fp32 re-rank).
+// *queries_ok_host = 0 (and nothing written) when byte points meet queries that are not integer-valued in the
+// storage's range; the caller then takes the exact float scan.
+int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
+                cudaStream_t st, int* queries_ok_host) {
+    const bool is_float = pts->storage == GPANN_STORAGE_F32;
     const int is_signed = pts->storage == GPANN_STORAGE_S8;
     const int d = (int) pts->d;
-    const size_t batch_max = (size_t) ctx->num_sms * tc::kMaxR * tc::kTileM;
+    const int kblocks = is_float ? pts->dp / 64 : 1;
+    // shared-memory plan: bytes / one K block: 4 Q tiles, 3 stages, 1024-deep queues; two K blocks: 2, 2, 512
+    const int max_r = kblocks == 1 ? tc::kMaxR : 2;
+    const int stages = kblocks == 1 ? 3 : 2;
+    const int qcap = kblocks == 1 ? 1024 : 512;
+    const size_t batch_max = (size_t) ctx->num_sms * max_r * tc::kTileM;
     *queries_ok_host = 1;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
         const size_t nqb = std::min(batch_max, nq - q0);
-        const int R = (int) std::min<size_t>(tc::kMaxR, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
+        const int R = (int) std::min<size_t>(max_r, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
         const int G = (int) ((nqb + (size_t) R * tc::kTileM - 1) / ((size_t) R * tc::kTileM));
         const uint32_t tiles_total = (uint32_t) (pts->n_pad / tc::kTileN);
         const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / G), tiles_total));
         const size_t nq_pad = (size_t) G * R * tc::kTileM;
         const int cap = std::max(128, pow2_ceil(k + 64));
-        GP_TRY(reserve(ctx, ctx->qrows, nq_pad * tc::kRowBytes));
+        const size_t qrow_bytes = is_float ? (size_t) pts->dp * 2 : tc::kRowBytes;
+        GP_TRY(reserve(ctx, ctx->qrows, nq_pad * qrow_bytes));
         GP_TRY(reserve(ctx, ctx->qnorm, nq_pad * 4));
         GP_TRY(reserve(ctx, ctx->bound, nq_pad * 4));
         GP_TRY(reserve(ctx, ctx->flags, 64));
         GP_TRY(reserve(ctx, ctx->cand, (size_t) G * S * R * tc::kTileM * cap * sizeof(uint64_t)));
         GP_TRY(reserve(ctx, ctx->partial, (size_t) S * nq_pad * k * sizeof(uint64_t)));
-        int one = 1;
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
-        launch_prep_queries_bytes(dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p,
-                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
-        GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
-        int ok = 0;
-        CU_TRY(ctx, cudaMemcpyAsync(&ok, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        if (!ok) {
-            *queries_ok_host = 0;
-            return 0;
+        if (is_float) {
+            GP_TRY(reserve(ctx, ctx->qf32, nq_pad * d * sizeof(float)));
+            launch_prep_queries_bf16(dq + q0 * d, (int) nqb, d, pts->dp, (int) nq_pad, (unsigned short*) ctx->qrows.p,
+                                     (float*) ctx->qnorm.p, (float*) ctx->qf32.p, (uint32_t*) ctx->bound.p, st);
+            GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
+        } else {
+            int one = 1;
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
+            launch_prep_queries_bytes(dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p,
+                                      (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
+            GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
+            int ok = 0;
+            CU_TRY(ctx, cudaMemcpyAsync(&ok, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            if (!ok) {
+                *queries_ok_host = 0;
+                return 0;
+            }
         }
         CUtensorMap tmap_q;
-        GP_TRY(encode_rows_map(ctx, &tmap_q, ctx->qrows.p, nq_pad, tc::kTileM, "queries"));
+        GP_TRY(encode_rows_map(ctx, &tmap_q, ctx->qrows.p, nq_pad, tc::kTileM, "queries", is_float, is_float ? pts->dp : tc::kRowBytes));
         tc::Args a;
+        std::memset(&a, 0, sizeof(a));
         a.pnorm = pts->t_norms;
         a.pid = pts->t_ids;
-        a.qnorm = (const int32_t*) ctx->qnorm.p;
+        a.qnorm = ctx->qnorm.p;
         a.R = R;
         a.G = G;
         a.S = S;
-        a.nks = (d + 31) / 32;
+        a.nks = is_float ? (d + 15) / 16 : (d + 31) / 32;
+        a.kblocks = kblocks;
+        a.stages = stages;
+        a.qcap = qcap;
         a.k = k;
         a.cap = cap;
-        a.idesc = tc::make_idesc_i8(is_signed);
+        a.idesc = is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(is_signed);
         a.cand = (uint64_t*) ctx->cand.p;
         a.partial = (uint64_t*) ctx->partial.p;
         a.bound = (uint32_t*) ctx->bound.p;
         a.mode = ctx->tc_mode;
+        a.rows_f32 = is_float ? (const float*) pts->rows : nullptr;
+        a.q_f32 = is_float ? (const float*) ctx->qf32.p : nullptr;
+        a.d = d;
+        a.id_base = pts->id_base;
+        a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
         const unsigned grid = (unsigned) (G * S);
-        const size_t smem = tc::smem_bytes(R);
+        const size_t smem = tc::smem_bytes(R, kblocks, stages, qcap);
         // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
         // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
         // (a cold start pushes EVERY distance through the selection warps).  Two levels: 1 tile per split (cold, but
@@ -333,8 +410,8 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
                 a.ntiles = nsample;
                 a.tile_stride = tiles_total / nsample;
                 a.tile_lo = a.tile_stride / 2;
-                launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
-                GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel(sample)"));
+                launch_topk_tc(is_float, pts->tmap, tmap_q, a, grid, smem, st);
+                GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
                 TopkOut b;
                 b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
                 b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
@@ -345,15 +422,15 @@ int topk_tensor_bytes(gpann_ctx* ctx, const gpann_points* pts, const float* dq, 
         a.tile_stride = 1;
         a.ntiles = tiles_total;
         if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-        launch_topk_tc_bytes(pts->tmap, tmap_q, a, grid, smem, st);
+        launch_topk_tc(is_float, pts->tmap, tmap_q, a, grid, smem, st);
         if (ctx->timing) {
             cudaEventRecord(ctx->ev1, st);
             ctx->timed = true;
         }
-        GP_TRY(check_launch(ctx, "topk_tc_bytes_kernel"));
+        GP_TRY(check_launch(ctx, "topk_tc_kernel"));
         GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, out, q0, st));
     }
-    ctx->last_algo = pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8";
+    ctx->last_algo = is_float ? "tensor_bf16" : (is_signed ? "tensor_s8" : "tensor_u8");
     return 0;
 }
 
@@ -365,12 +442,17 @@ int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, siz
     if (row_begin > row_end || row_end > pts->n) return fail(ctx, GPANN_E_ARG, "topk: bad row range");
     if (nq == 0) return 0;
     const bool full = row_begin == 0 && row_end == pts->n;
-    const bool tensor_ok = pts->has_tensor && metric == GPANN_METRIC_L2 && full && k <= 448;
+    const bool is_float = pts->storage == GPANN_STORAGE_F32;
+    const bool want_tensor = metric == GPANN_METRIC_L2 && full && k <= 448 &&
+                             (ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16 && (!is_float || pts->n >= 4096)));
+    if (want_tensor && is_float && !pts->tensor_tried)  // lazily build the bf16 layout (handle state, not query state)
+        GP_TRY(build_tensor_float(ctx, const_cast<gpann_points*>(pts), st));
+    const bool tensor_ok = want_tensor && pts->has_tensor;
     if (ctx->algo == GPANN_ALGO_TENSOR && !tensor_ok)
-        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs byte storage with d<=128, L2, full range, k<=448");
-    if (tensor_ok && (ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16))) {
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs d<=128, L2, full range, k<=448");
+    if (tensor_ok) {
         int ok = 1;
-        GP_TRY(topk_tensor_bytes(ctx, pts, dq, nq, k, out, st, &ok));
+        GP_TRY(topk_tensor(ctx, pts, dq, nq, k, out, st, &ok));
         if (ok) return 0;
         if (ctx->algo == GPANN_ALGO_TENSOR)
             return fail(ctx, GPANN_E_UNSUPPORTED, "topk: queries are not integer-valued in the storage range");
@@ -548,7 +630,7 @@ void gpann_destroy(gpann_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->bound, &ctx->flags, &ctx->dist_out,
+    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign };
     for (DevBuf* b : bufs) release(*b);

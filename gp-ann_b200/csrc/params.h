@@ -84,36 +84,44 @@ struct ObjectiveParams {
 namespace tc {
 constexpr int kTileN = 256;       // points per tile  (UMMA N)
 constexpr int kTileM = 128;       // queries per tile (UMMA M)
-constexpr int kRowBytes = 128;    // operand row bytes = one SWIZZLE_128B row
-constexpr int kStages = 3;
+constexpr int kRowBytes = 128;    // bytes of one K block of an operand row = one SWIZZLE_128B row
+constexpr int kMaxStages = 3;
 constexpr int kMaxR = 4;
-constexpr int kEpiWarps = 8;                     // filter warps (two groups of 4, one per TMEM accumulator slot)
+constexpr int kMaxKBlocks = 2;    // K blocks of 128 bytes per row: bytes d <= 128 -> 1; bf16 d <= 64 -> 1, d <= 128 -> 2
+constexpr int kEpiWarps = 8;                     // filter warps: 4 TMEM lane quadrants x 2 column halves
 constexpr int kSelWarps = 2;                     // selection warps (own the per-query top-k lists)
-constexpr int kQueueCap = 1024;                  // records per candidate queue (one queue per selection warp)
-constexpr int kThreads = 64 + 32 * (kEpiWarps + kSelWarps);  // warp 0: TMA, warp 1: MMA, epilogue, selection
-constexpr int kQTileBytes = kTileM * kRowBytes;  // 16 KB
-constexpr int kPTileBytes = kTileN * kRowBytes;  // 32 KB
+constexpr int kThreads = 64 + 32 * (kEpiWarps + kSelWarps);  // warp 0: TMA, warp 1: MMA, filter, selection
+constexpr int kQBlockBytes = kTileM * kRowBytes;  // 16 KB per K block of a query tile
+constexpr int kPBlockBytes = kTileN * kRowBytes;  // 32 KB per K block of a point tile
 constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
 
 struct Args {
-    const int32_t* pnorm;    // [n_pad] ascending
+    const void* pnorm;       // [n_pad] ascending squared norms: int32 (bytes) or float (bf16 path)
     const uint32_t* pid;     // [n_pad] original ids, kInvalidId on padding rows
-    const int32_t* qnorm;    // [G*R*128]
+    const void* qnorm;       // [G*R*128] squared query norms, same type as pnorm
     int R, G, S;             // Q tiles per CTA (1..4), query groups, point splits
-    int nks;                 // K steps of 32 bytes
-    int k, cap;              // top-k and candidate buffer capacity (power of two >= k + 64)
+    int nks;                 // K steps of 32 bytes (32 byte elements or 16 bf16 elements)
+    int kblocks, stages;     // 128-byte K blocks per row; depth of the point-tile ring
+    int qcap;                // records per candidate queue (power of two)
+    int k, cap;              // top-k and per-query list capacity (power of two >= k + 64)
     uint32_t tile_lo, tile_stride, ntiles;  // this launch scans tiles tile_lo + i*tile_stride, i in [0,ntiles)
     uint32_t idesc;          // tcgen05 instruction descriptor
     uint64_t* cand;          // [grid, R*128, cap] per-query key lists (global, touched by the selection warps only)
     uint64_t* partial;       // [S, G*R*128, k]
-    uint32_t* bound;         // [G*R*128] shared upper bound on each query's kth distance (ordered-float bits)
+    uint32_t* bound;         // [G*R*128] upper bound on each query's kth distance from the sample passes (float bits)
     int mode;                // 0 = full; probes with invalid results: 1 = MMA + TMEM loads + max, 2 = MMA issue only
+    // float path only: the exact re-rank reads the original fp32 rows
+    const float* rows_f32;   // [n, d] original point rows
+    const float* q_f32;      // [G*R*128, d] queries (zero padded)
+    int d;
+    uint32_t id_base;
+    float eps;               // relative error bound of the bf16 dot product: |dot~ - dot| <= eps*|q|*|x|
 };
 
-// Shared-memory footprint for R resident Q tiles (+1 KB so the operand area can be aligned to 1024 bytes).
-inline size_t smem_bytes(int R) {
-    return 1024 + (size_t) R * kQTileBytes + (size_t) kStages * kPTileBytes + 256 /*barriers, counters*/ +
-           (size_t) kStages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * kQueueCap * 12 /*queues*/ +
+// Shared-memory footprint (+1 KB so the operand area can be aligned to 1024 bytes).
+inline size_t smem_bytes(int R, int kblocks, int stages, int qcap) {
+    return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
+           (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 12 /*queues*/ +
            (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {
@@ -121,6 +129,11 @@ inline uint32_t make_idesc_i8(bool is_signed) {
     return (2u << 4)                    // D format: S32
            | (fmt << 7) | (fmt << 10)   // A, B format: 0 = u8, 1 = s8
            | ((uint32_t) (kTileN >> 3) << 17) | ((uint32_t) (kTileM >> 4) << 24);  // both operands K-major
+}
+inline uint32_t make_idesc_bf16() {
+    return (1u << 4)                    // D format: F32
+           | (1u << 7) | (1u << 10)     // A, B format: BF16
+           | ((uint32_t) (kTileN >> 3) << 17) | ((uint32_t) (kTileM >> 4) << 24);
 }
 }  // namespace tc
 
@@ -153,8 +166,15 @@ void launch_gather_sorted_rows(const unsigned char* rows, size_t n, int d, size_
                                int32_t* out_norms, uint32_t* out_ids, int blocks, cudaStream_t st);
 void launch_prep_queries_bytes(const float* q, int nq, int d, int nq_pad, int is_signed, unsigned char* out_rows,
                                int32_t* out_norms, int* ok, uint32_t* bound, cudaStream_t st);
+// float tensor layout: norms, norm-sorted bf16 rows (dp = padded row length in elements), query preparation
+void launch_float_norms(const float* rows, size_t n, int d, uint32_t* norm_bits, uint32_t* index, int blocks, cudaStream_t st);
+void launch_gather_sorted_rows_bf16(const float* rows, size_t n, int d, int dp, const uint32_t* perm, const uint32_t* sorted_norm_bits,
+                                    uint32_t id_base, size_t n_pad, unsigned short* out_rows, float* out_norms, uint32_t* out_ids,
+                                    int blocks, cudaStream_t st);
+void launch_prep_queries_bf16(const float* q, int nq, int d, int dp, int nq_pad, unsigned short* out_rows, float* out_norms,
+                              float* out_q_f32, uint32_t* bound, cudaStream_t st);
 
-void launch_topk_tc_bytes(const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid, size_t smem,
-                          cudaStream_t st);
+void launch_topk_tc(bool is_float, const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid,
+                    size_t smem, cudaStream_t st);
 
 }  // namespace gpann

@@ -104,6 +104,65 @@ __global__ void prep_queries_bytes_kernel(const float* q, int nq, int d, int nq_
     }
 }
 
+// ---- float tensor layout (bf16 filter operands + fp32 norms), see topk_tc.cu --------------------------------------
+// Squared norm of float rows in fp32 (plain sequential sum; the filter's slack covers its rounding), emitted as
+// the float's bit pattern: norms are >= 0, so the unsigned bit order is the numeric order (radix-sort key).
+__global__ void float_norms_kernel(const float* rows, size_t n, int d, uint32_t* norm_bits, uint32_t* index) {
+    for (size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (size_t) gridDim.x * blockDim.x) {
+        const float* row = rows + r * d;
+        float acc = 0.f;
+        for (int j = 0; j < d; ++j) acc = __fmaf_rn(row[j], row[j], acc);
+        norm_bits[r] = __float_as_uint(acc);
+        index[r] = (uint32_t) r;
+    }
+}
+
+__device__ __forceinline__ unsigned short f32_to_bf16_rn(float f) {  // round to nearest even
+    uint32_t u = __float_as_uint(f);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (unsigned short) (u >> 16);
+}
+
+// Gather float rows into norm order as bf16 rows of dp elements (zero padded); rows >= n are zero padding with
+// id = kInvalidId and a huge norm.  One warp per output row.
+__global__ void gather_sorted_rows_bf16_kernel(const float* rows, size_t n, int d, int dp, const uint32_t* perm,
+                                               const uint32_t* sorted_norm_bits, uint32_t id_base, size_t n_pad,
+                                               unsigned short* out_rows, float* out_norms, uint32_t* out_ids) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t) gridDim.x * blockDim.x) >> 5;
+    for (size_t r = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_pad; r += warps) {
+        const float* src = r < n ? rows + (size_t) perm[r] * d : nullptr;
+        for (int j = lane; j < dp; j += 32) out_rows[r * dp + j] = (src && j < d) ? f32_to_bf16_rn(src[j]) : (unsigned short) 0;
+        if (lane == 0) {
+            out_norms[r] = r < n ? __uint_as_float(sorted_norm_bits[r]) : 3.0e38f;
+            out_ids[r] = r < n ? id_base + perm[r] : kInvalidId;
+        }
+    }
+}
+
+// Queries for the bf16 tensor kernel: float [nq,d] -> bf16 rows [nq_pad,dp], fp32 norms, a zero-padded fp32 copy
+// for the exact re-rank, and the warm-start bounds reset to +inf.
+__global__ void prep_queries_bf16_kernel(const float* q, int nq, int d, int dp, int nq_pad, unsigned short* out_rows,
+                                         float* out_norms, float* out_q_f32, uint32_t* bound) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nq_pad; r += warps) {
+        float nrm = 0.f;
+        for (int j = lane; j < dp; j += 32) {
+            const float v = (r < nq && j < d) ? q[(size_t) r * d + j] : 0.f;
+            out_rows[(size_t) r * dp + j] = f32_to_bf16_rn(v);
+            if (j < d) out_q_f32[(size_t) r * d + j] = v;
+            nrm = __fmaf_rn(v, v, nrm);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        if (lane == 0) {
+            out_norms[r] = nrm;
+            bound[r] = 0x7f800000u;
+        }
+    }
+}
+
 void launch_detect_bytes(const float* x, size_t count, int* flags, int blocks, cudaStream_t st) {
     detect_bytes_kernel<<<blocks, 256, 0, st>>>(x, count, flags);
 }
@@ -124,6 +183,22 @@ void launch_prep_queries_bytes(const float* q, int nq, int d, int nq_pad, int is
                                int* ok, uint32_t* bound, cudaStream_t st) {
     const unsigned blocks = (unsigned) ((((size_t) nq_pad * 32 + 255) / 256) < 1024 ? (((size_t) nq_pad * 32 + 255) / 256) : 1024);
     prep_queries_bytes_kernel<<<blocks, 256, 0, st>>>(q, nq, d, nq_pad, is_signed, out_rows, out_norms, ok, bound);
+}
+
+void launch_float_norms(const float* rows, size_t n, int d, uint32_t* norm_bits, uint32_t* index, int blocks, cudaStream_t st) {
+    float_norms_kernel<<<blocks, 256, 0, st>>>(rows, n, d, norm_bits, index);
+}
+void launch_gather_sorted_rows_bf16(const float* rows, size_t n, int d, int dp, const uint32_t* perm, const uint32_t* sorted_norm_bits,
+                                    uint32_t id_base, size_t n_pad, unsigned short* out_rows, float* out_norms, uint32_t* out_ids,
+                                    int blocks, cudaStream_t st) {
+    gather_sorted_rows_bf16_kernel<<<blocks, 256, 0, st>>>(rows, n, d, dp, perm, sorted_norm_bits, id_base, n_pad, out_rows, out_norms,
+                                                           out_ids);
+}
+void launch_prep_queries_bf16(const float* q, int nq, int d, int dp, int nq_pad, unsigned short* out_rows, float* out_norms,
+                              float* out_q_f32, uint32_t* bound, cudaStream_t st) {
+    const size_t want = ((size_t) nq_pad * 32 + 255) / 256;
+    prep_queries_bf16_kernel<<<(unsigned) (want < 1024 ? want : 1024), 256, 0, st>>>(q, nq, d, dp, nq_pad, out_rows, out_norms, out_q_f32,
+                                                                                     bound);
 }
 
 }  // namespace gpann

@@ -18,6 +18,12 @@
 // k <= 32, append + warp-wide bitonic compaction above) and publish the tightened threshold back through shared
 // memory.  The tensor pipeline (TMA -> MMA -> TMEM drain) therefore never waits for selection work.
 //
+// FLOAT DATA (kFloat = true): the same pipeline with bf16 operands (tcgen05.mma.kind::f16, fp32 accumulate) as a
+// conservative FILTER: |dot_bf16 - dot| <= eps*|q|*|x| (operand rounding 2^-8 each + fp32 accumulation), so every point
+// whose fp32 distance can be <= kth_q satisfies  acc >= T_q(tile)  with the error bound folded into T.  Survivors are
+// re-ranked EXACTLY: the selection warp recomputes the distance from the original fp32 rows in the reference's own
+// summation order (src/dist.cpp:9-16), so reported distances and tie-breaks are those of the CPU code.
+//
 // CTA roles (384 threads, 1 CTA/SM, persistent over its point range):
 //   warp 0 lane 0 : TMA producer -- Q tiles once, then per point tile 256x128B rows (SWIZZLE_128B) + its 256 norms
 //                                   + 256 ids into a kStages ring, all on one mbarrier
@@ -109,6 +115,14 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -138,27 +152,39 @@ __device__ __forceinline__ int max32(const uint32_t (&v)[32]) {
     return max(max3(b0, b1, b2), b3);
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // -> FMNMX3
+__device__ __forceinline__ float max32f(const uint32_t (&v)[32]) {
+    float a[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        a[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float b0 = fmax3(a[0], a[1], a[2]), b1 = fmax3(a[3], a[4], a[5]), b2 = fmax3(a[6], a[7], a[8]), b3 = fmaxf(a[9], a[10]);
+    return fmaxf(fmax3(b0, b1, b2), b3);
+}
+
 // ---- candidate queues: epilogue lanes push (key, query slot) records, a selection warp pops them ------------------
 // Single consumer per queue; a slot's qs word doubles as its ready flag (kQEmpty = free).
 constexpr uint32_t kQEmpty = 0xFFFFFFFFu;
 
 struct Queue {
-    uint64_t* key;            // [kQueueCap]
-    volatile uint32_t* qs;    // [kQueueCap]
+    uint32_t cap;             // records (power of two)
+    uint64_t* key;            // [cap]
+    volatile uint32_t* qs;    // [cap]
     uint32_t* tail;           // reserved by producers (atomicAdd)
     volatile uint32_t* head;  // consumed (written by the consumer's lane 0)
 };
 
 __device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs) {
     const uint32_t pos = atomicAdd(q.tail, 1u);
-    if (pos - *q.head >= (uint32_t) kQueueCap) {  // full: wait for the selection warp (rare)
+    if (pos - *q.head >= q.cap) {  // full: wait for the selection warp (rare)
         const uint64_t t0 = global_timer_ns();
-        while (pos - *q.head >= (uint32_t) kQueueCap) {
+        while (pos - *q.head >= q.cap) {
             __nanosleep(64);
             if (global_timer_ns() - t0 > 4000000000ull) __trap();
         }
     }
-    const uint32_t slot = pos & (kQueueCap - 1);
+    const uint32_t slot = pos & (q.cap - 1);
     q.key[slot] = key;
     __threadfence_block();
     q.qs[slot] = qs;
@@ -181,6 +207,19 @@ __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, co
     }
 }
 
+// Float variant: the record carries the point id only (the approximate distance is not good enough to rank); the
+// selection warp recomputes the exact fp32 distance.
+__device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T, const uint32_t* ti, int col0, uint32_t qs,
+                                                const Queue& q) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (__uint_as_float(v[j]) >= T) {
+            const uint32_t id = ti[col0 + j];
+            if (id != kInvalidId) queue_push(q, (uint64_t) id, qs);
+        }
+    }
+}
+
 // Per-query selection state owned by the selection warps (shared memory, indexed by query slot qs).
 struct SelState {
     uint64_t* kth;   // current k-th best key (kEmptyKey until k keys are held)
@@ -190,11 +229,74 @@ struct SelState {
     const int* nq;   // |q|^2
     uint64_t* lists; // global: [nslots][cap] keys of this CTA
     int k, cap;
+    // float path: exact re-rank inputs
+    const float* rows_f32;  // [n, d]
+    const float* q_f32;     // this CTA's queries [nslots, d]
+    int d;
+    uint32_t id_base;
 };
+
+// Squared L2 distance of two fp32 rows in the reference's summation order (src/dist.cpp:9-16 ->
+// hnswlib space_l2.h:60-91, 6-20): 8 interleaved FMA lanes over the leading multiple of 16, lanes added in order, then
+// a sequential FMA tail.
+__device__ __forceinline__ float exact_sqr_l2(const float* __restrict__ x, const float* __restrict__ q, int d) {
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f, l5 = 0.f, l6 = 0.f, l7 = 0.f;
+    const int d16 = d & ~15;
+    if ((d & 3) == 0) {  // rows are 16-byte aligned
+        for (int i = 0; i < d16; i += 8) {
+            const float4 xa = __ldg(reinterpret_cast<const float4*>(x + i)), xb = __ldg(reinterpret_cast<const float4*>(x + i + 4));
+            const float4 qa = __ldg(reinterpret_cast<const float4*>(q + i)), qb = __ldg(reinterpret_cast<const float4*>(q + i + 4));
+            float t;
+            t = xa.x - qa.x; l0 = __fmaf_rn(t, t, l0);
+            t = xa.y - qa.y; l1 = __fmaf_rn(t, t, l1);
+            t = xa.z - qa.z; l2 = __fmaf_rn(t, t, l2);
+            t = xa.w - qa.w; l3 = __fmaf_rn(t, t, l3);
+            t = xb.x - qb.x; l4 = __fmaf_rn(t, t, l4);
+            t = xb.y - qb.y; l5 = __fmaf_rn(t, t, l5);
+            t = xb.z - qb.z; l6 = __fmaf_rn(t, t, l6);
+            t = xb.w - qb.w; l7 = __fmaf_rn(t, t, l7);
+        }
+    } else {
+        for (int i = 0; i < d16; i += 8) {
+            float t;
+            t = x[i + 0] - q[i + 0]; l0 = __fmaf_rn(t, t, l0);
+            t = x[i + 1] - q[i + 1]; l1 = __fmaf_rn(t, t, l1);
+            t = x[i + 2] - q[i + 2]; l2 = __fmaf_rn(t, t, l2);
+            t = x[i + 3] - q[i + 3]; l3 = __fmaf_rn(t, t, l3);
+            t = x[i + 4] - q[i + 4]; l4 = __fmaf_rn(t, t, l4);
+            t = x[i + 5] - q[i + 5]; l5 = __fmaf_rn(t, t, l5);
+            t = x[i + 6] - q[i + 6]; l6 = __fmaf_rn(t, t, l6);
+            t = x[i + 7] - q[i + 7]; l7 = __fmaf_rn(t, t, l7);
+        }
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(l0, l1), l2), l3), l4), l5), l6), l7);
+    float tail = 0.f;
+    for (int i = d16; i < d; ++i) {
+        const float t = x[i] - q[i];
+        tail = __fmaf_rn(t, t, tail);
+    }
+    return __fadd_rn(res, tail);
+}
 
 // Insert one record.  k <= 32: unsorted list of the k best with replace-the-maximum (exact threshold after every
 // insert).  Larger k: append; the caller compacts a full list warp-wide.  Returns true if the list needs compaction.
+template <bool kFloat>
+__device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs, uint64_t kth) {
+    if (kFloat) {  // U = |q|^2 - kth (float bits in the int arrays); monotone non-decreasing
+        const float u = __int_as_float(s.nq[qs]) - key_dist(kth);
+        s.U[qs] = __float_as_int(fmaxf(__int_as_float(s.U[qs]), u));
+    } else {
+        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) key_dist(kth));
+    }
+}
+
+template <bool kFloat>
 __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key) {
+    if (kFloat) {  // the record holds the id: compute the exact distance now
+        const uint32_t id = (uint32_t) key;
+        const float dist = exact_sqr_l2(s.rows_f32 + (size_t) (id - s.id_base) * s.d, s.q_f32 + (size_t) qs * s.d, s.d);
+        key = pack_key(dist, id);
+    }
     uint64_t* list = s.lists + (size_t) qs * s.cap;
     int cnt = s.cnt[qs];
     if (s.k <= 32) {
@@ -217,7 +319,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         }
         s.kth[qs] = m;
         s.maxpos[qs] = mp;
-        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) key_dist(m));
+        publish_threshold<kFloat>(s, qs, m);
         return false;
     }
     if (key >= s.kth[qs]) return false;
@@ -226,6 +328,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     return cnt >= s.cap;
 }
 
+template <bool kFloat>
 __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane) {
     uint32_t head = 0;
     while (true) {
@@ -243,7 +346,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         uint64_t key = 0;
         bool pending = (uint32_t) lane < n;
         if (pending) {
-            const uint32_t slot = (head + lane) & (kQueueCap - 1);
+            const uint32_t slot = (head + lane) & (q.cap - 1);
             uint32_t w = q.qs[slot];
             if (w == kQEmpty) {
                 const uint64_t t0 = global_timer_ns();
@@ -265,7 +368,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             bool compact = false;
             if (pending && (__ffs(peers) - 1) == lane) {
-                compact = select_insert(s, qs, key);
+                compact = select_insert<kFloat>(s, qs, key);
                 pending = false;
             }
             __syncwarp();
@@ -279,7 +382,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                 if (lane == L) {
                     s.cnt[qsL] = s.k;
                     s.kth[qsL] = newkth;
-                    s.U[qsL] = max(s.U[qsL], s.nq[qsL] - (int) key_dist(newkth));
+                    publish_threshold<kFloat>(s, qsL, newkth);
                 }
                 __syncwarp();
             }
@@ -287,58 +390,66 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
     }
 }
 
+template <bool kFloat>
 __global__ void __launch_bounds__(kThreads, 1)
-topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q, const Args a) {
+topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q, const Args a) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int R = a.R;
+    const int R = a.R, KB = a.kblocks, NST = a.stages;
     const int g = blockIdx.x % a.G, s = blockIdx.x / a.G;
     // logical tile indices [tile_begin, tile_end) of this split; physical tile = tile_lo + index * tile_stride
     const uint32_t tile_begin = (uint32_t) (((uint64_t) a.ntiles * s) / a.S);
     const uint32_t tile_end = (uint32_t) (((uint64_t) a.ntiles * (s + 1)) / a.S);
+    const uint32_t q_tile_bytes = (uint32_t) KB * kQBlockBytes, p_tile_bytes = (uint32_t) KB * kPBlockBytes;
 
     // ---- carve shared memory (operand tiles 1024-byte aligned for SWIZZLE_128B) ----
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
     unsigned char* base = smem_raw + pad;
     const uint32_t sQ = raw_addr + pad;
-    const uint32_t sP = sQ + R * kQTileBytes;
-    unsigned char* after = base + (size_t) R * kQTileBytes + (size_t) kStages * kPTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(after);  // full[kStages], empty[kStages], qfull, tfull[2], tempty[2]
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages, bar_q = bar_empty + 8 * kStages,
+    const uint32_t sP = sQ + R * q_tile_bytes;
+    unsigned char* after = base + (size_t) R * q_tile_bytes + (size_t) NST * p_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(after);  // full[3], empty[3], qfull, tfull[2], tempty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages, bar_q = bar_empty + 8 * kMaxStages,
                    bar_tfull = bar_q + 8, bar_tempty = bar_tfull + 16;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 8 * (2 * kStages + 5));
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 8 * (2 * kMaxStages + 5));
     uint32_t* s_ctr = reinterpret_cast<uint32_t*>(after + 128);               // q_tail[2], q_head[2], done
-    int32_t* s_norm = reinterpret_cast<int32_t*>(after + 256);                 // [kStages][256]
-    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_norm + kStages * kTileN);   // [kStages][256]
-    uint64_t* s_kth = reinterpret_cast<uint64_t*>(s_id + kStages * kTileN);    // [R*128]
-    uint64_t* s_qkey = s_kth + R * kTileM;                                     // [kSelWarps][kQueueCap]
-    uint32_t* s_qqs = reinterpret_cast<uint32_t*>(s_qkey + kSelWarps * kQueueCap);  // [kSelWarps][kQueueCap]
-    int* s_U = reinterpret_cast<int*>(s_qqs + kSelWarps * kQueueCap);          // [R*128]
+    int32_t* s_norm = reinterpret_cast<int32_t*>(after + 256);                 // [NST][256] int32 or float bits
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_norm + NST * kTileN);       // [NST][256]
+    uint64_t* s_kth = reinterpret_cast<uint64_t*>(s_id + NST * kTileN);        // [R*128]
+    uint64_t* s_qkey = s_kth + R * kTileM;                                     // [kSelWarps][qcap]
+    uint32_t* s_qqs = reinterpret_cast<uint32_t*>(s_qkey + kSelWarps * a.qcap);  // [kSelWarps][qcap]
+    int* s_U = reinterpret_cast<int*>(s_qqs + kSelWarps * a.qcap);             // [R*128] int or float bits
     int* s_cnt = s_U + R * kTileM;
-    int* s_nq = s_cnt + R * kTileM;
+    int* s_nq = s_cnt + R * kTileM;                                            // int or float bits
     int* s_maxpos = s_nq + R * kTileM;
 
     const int nslots = R * kTileM;
     const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
     for (int i = tid; i < nslots; i += kThreads) {
-        const int nqv = a.qnorm[qbase + i];
         s_kth[i] = kEmptyKey;
         s_cnt[i] = 0;
         s_maxpos[i] = 0;
-        s_nq[i] = nqv;
-        // warm start: an upper bound on this query's kth distance from the sample pre-pass (+inf = none)
+        // warm start: an upper bound on this query's kth distance from the sample passes (+inf = none)
         const float b = a.bound ? __uint_as_float(a.bound[qbase + i]) : __int_as_float(0x7f800000);
-        s_U[i] = (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
+        if (kFloat) {
+            const float nqv = reinterpret_cast<const float*>(a.qnorm)[qbase + i];
+            s_nq[i] = __float_as_int(nqv);
+            s_U[i] = __float_as_int((b < 3.0e38f) ? nqv - b : -3.0e38f);
+        } else {
+            const int nqv = reinterpret_cast<const int32_t*>(a.qnorm)[qbase + i];
+            s_nq[i] = nqv;
+            s_U[i] = (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
+        }
     }
-    for (int i = tid; i < kSelWarps * kQueueCap; i += kThreads) s_qqs[i] = kQEmpty;
+    for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qqs[i] = kQEmpty;
     if (tid < 8) s_ctr[tid] = 0;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_p);
         prefetch_tmap(&tmap_q);
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1 + kEpiWarps);  // MMA commit + every epilogue warp done with the tile
+            mbar_init(bar_empty + 8 * i, 1 + kEpiWarps);  // MMA commit + every filter warp done with the tile
         }
         mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) {
@@ -358,19 +469,24 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
     tcgen05_fence_after();
     const uint32_t tmem_base = *s_tmem;
     uint64_t* my_lists = a.cand + (size_t) blockIdx.x * nslots * a.cap;
+    const int kb_elems = kFloat ? 64 : 128;  // elements per 128-byte K block
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            mbar_expect_tx(bar_q, (uint32_t) (R * kQTileBytes));
-            for (int r = 0; r < R; ++r) tma_load_2d(sQ + r * kQTileBytes, &tmap_q, bar_q, 0, (int) ((g * R + r) * kTileM));
+            mbar_expect_tx(bar_q, (uint32_t) R * q_tile_bytes);
+            for (int r = 0; r < R; ++r)
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sQ + r * q_tile_bytes + kb * kQBlockBytes, &tmap_q, bar_q, kb * kb_elems, (int) ((g * R + r) * kTileM));
             for (uint32_t t = tile_begin; t < tile_end; ++t) {
-                const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+                const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
                 mbar_wait(bar_empty + 8 * st, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * st, kPTileBytes + 2 * kTileN * 4);
+                mbar_expect_tx(bar_full + 8 * st, p_tile_bytes + 2 * kTileN * 4);
                 const size_t row0 = ((size_t) a.tile_lo + (size_t) t * a.tile_stride) * kTileN;
-                tma_load_2d(sP + st * kPTileBytes, &tmap_p, bar_full + 8 * st, 0, (int) row0);
-                bulk_load_1d(smem_u32(s_norm + st * kTileN), a.pnorm + row0, kTileN * 4, bar_full + 8 * st);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sP + st * p_tile_bytes + kb * kPBlockBytes, &tmap_p, bar_full + 8 * st, kb * kb_elems, (int) row0);
+                bulk_load_1d(smem_u32(s_norm + st * kTileN), reinterpret_cast<const int32_t*>(a.pnorm) + row0, kTileN * 4,
+                             bar_full + 8 * st);
                 bulk_load_1d(smem_u32(s_id + st * kTileN), a.pid + row0, kTileN * 4, bar_full + 8 * st);
             }
         }
@@ -381,26 +497,30 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
             tcgen05_fence_after();
             uint32_t it = 0;
             for (uint32_t t = tile_begin; t < tile_end; ++t) {
-                const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+                const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
                 mbar_wait(bar_full + 8 * st, ph);
                 tcgen05_fence_after();
-                const uint64_t bdesc = make_sw128_desc(sP + st * kPTileBytes);
                 for (int r = 0; r < R; ++r, ++it) {
                     const uint32_t slot = it & 1, sph = (it >> 1) & 1;
                     mbar_wait(bar_tempty + 8 * slot, sph ^ 1);
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_sw128_desc(sQ + r * kQTileBytes);
                     const uint32_t dcol = tmem_base + slot * kTileN;
-                    for (int ks = 0; ks < a.nks; ++ks)  // +32 bytes of K per step = +2 in 16-byte units
-                        umma_i8(dcol, adesc + 2 * ks, bdesc + 2 * ks, a.idesc, ks > 0 ? 1u : 0u);
-                    umma_commit(bar_tfull + 8 * slot);  // accumulator ready for the epilogue
+                    for (int ks = 0; ks < a.nks; ++ks) {
+                        // K step ks = 32 bytes: block ks/4 of the row, +2 (16-byte units) per step inside the block
+                        const int kb = ks >> 2, w = ks & 3;
+                        const uint64_t adesc = make_sw128_desc(sQ + r * q_tile_bytes + kb * kQBlockBytes) + 2 * w;
+                        const uint64_t bdesc = make_sw128_desc(sP + st * p_tile_bytes + kb * kPBlockBytes) + 2 * w;
+                        if (kFloat) umma_bf16(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
+                        else umma_i8(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_tfull + 8 * slot);  // accumulator ready for the filter warps
                 }
                 umma_commit(bar_empty + 8 * st);  // operands consumed (1 of 1+kEpiWarps arrivals)
             }
         }
     } else if (warp < 2 + kEpiWarps) {
-        // ===== epilogue (filter): every warp drains every item; warp (w & 3) owns TMEM lanes [32*(w&3), +32) and the
-        // column half (w-2)/4 of the 256-column accumulator =====
+        // ===== filter: every warp drains every item; warp (w & 3) owns TMEM lanes [32*(w&3), +32) and the column
+        // half (w-2)/4 of the 256-column accumulator =====
         const int ew = warp - 2;
         const int half = ew >> 2;
         const int wq = warp & 3;
@@ -409,21 +529,43 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         const int col_base = half * (kTileN / 2);
         uint32_t it = 0;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
-            const uint32_t tl = t - tile_begin, st = tl % kStages, ph = (tl / kStages) & 1;
+            const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
             mbar_wait(bar_full + 8 * st, ph);
             const int32_t* tn = s_norm + st * kTileN;
             const uint32_t* ti = s_id + st * kTileN;
-            const int nmin = tn[0];
+            // tile norm range (rows are sorted by norm): first and last row
+            const int nmin_i = tn[0];
+            const float nmin_f = __int_as_float(tn[0]), nmax_f = __int_as_float(tn[kTileN - 1]);
             for (int r = 0; r < R; ++r, ++it) {
                 const uint32_t slot = it & 1, sph = (it >> 1) & 1;
                 const uint32_t qs = (uint32_t) (r * kTileM + qrow);
-                const int T = (*reinterpret_cast<volatile int*>(s_U + qs) + nmin + 1) >> 1;
-                const int nqv = s_nq[qs];
+                const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
+                const int nqraw = s_nq[qs];
+                int Ti = 0;
+                float Tf = 0.f;
+                if (kFloat) {
+                    // keep x if  nq + nx - 2*dot~ - slack(nq,nx) <= kth,  slack = 2*eps*sqrt(nq*nx) + 1e-5*(nq+nx);
+                    // g(nx) = nx - slack is evaluated at both ends of the tile's norm range (it is monotone in between)
+                    const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
+                    const float sq = 2.f * a.eps * sqrtf(nqv);
+                    const float g0 = nmin_f - sq * sqrtf(nmin_f) - 1e-5f * (nqv + nmin_f);
+                    const float g1 = nmax_f - sq * sqrtf(nmax_f) - 1e-5f * (nqv + nmax_f);
+                    float gmin = fminf(g0, g1);
+                    // g is a convex parabola in sqrt(nx) with its minimum at nx* = (eps^2)*nq: if the tile straddles it
+                    // (points with norms far below the query's), use the global minimum instead of the end points
+                    const float nstar = a.eps * a.eps * nqv;
+                    if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
+                    Tf = 0.5f * (U + gmin);
+                    Tf -= 1e-6f * fabsf(Tf);
+                } else {
+                    Ti = (Uraw + nmin_i + 1) >> 1;
+                }
                 const int sel = (int) (qs >> 5) & (kSelWarps - 1);
                 Queue q;
-                q.key = s_qkey + sel * kQueueCap;
-                q.qs = s_qqs + sel * kQueueCap;
+                q.cap = (uint32_t) a.qcap;
+                q.key = s_qkey + sel * a.qcap;
+                q.qs = s_qqs + sel * a.qcap;
                 q.tail = s_ctr + sel;
                 q.head = s_ctr + kSelWarps + sel;
                 mbar_wait(bar_tfull + 8 * slot, sph);
@@ -443,15 +585,28 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                     tmem_ld32(tbase + c * 64, va);
                     tmem_ld32(tbase + c * 64 + 32, vb);
                     tmem_wait_ld();
-                    const int ma = max32(va), mb = max32(vb);
-                    if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
-                        if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
-                        continue;
-                    }
-                    if (__any_sync(0xffffffffu, max(ma, mb) >= T)) {
-                        if (ma >= T) enqueue_chunk(va, T, tn, ti, col_base + c * 64, nqv, qs, q);
-                        if (mb >= T) enqueue_chunk(vb, T, tn, ti, col_base + c * 64 + 32, nqv, qs, q);
-                        __syncwarp();
+                    if (kFloat) {
+                        const float ma = max32f(va), mb = max32f(vb);
+                        if (a.mode == 1) {
+                            if (fmaxf(ma, mb) == 3.0e38f) s_U[qs] = __float_as_int(ma);
+                            continue;
+                        }
+                        if (__any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
+                            if (ma >= Tf) enqueue_chunk_f(va, Tf, ti, col_base + c * 64, qs, q);
+                            if (mb >= Tf) enqueue_chunk_f(vb, Tf, ti, col_base + c * 64 + 32, qs, q);
+                            __syncwarp();
+                        }
+                    } else {
+                        const int ma = max32(va), mb = max32(vb);
+                        if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
+                            if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
+                            continue;
+                        }
+                        if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
+                            if (ma >= Ti) enqueue_chunk(va, Ti, tn, ti, col_base + c * 64, nqraw, qs, q);
+                            if (mb >= Ti) enqueue_chunk(vb, Ti, tn, ti, col_base + c * 64 + 32, nqraw, qs, q);
+                            __syncwarp();
+                        }
                     }
                 }
                 tcgen05_fence_before();
@@ -468,8 +623,9 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         // ===== selection warps: exact per-query top-k lists, thresholds published through s_U =====
         const int sel = warp - (2 + kEpiWarps);
         Queue q;
-        q.key = s_qkey + sel * kQueueCap;
-        q.qs = s_qqs + sel * kQueueCap;
+        q.cap = (uint32_t) a.qcap;
+        q.key = s_qkey + sel * a.qcap;
+        q.qs = s_qqs + sel * a.qcap;
         q.tail = s_ctr + sel;
         q.head = s_ctr + kSelWarps + sel;
         SelState ss;
@@ -481,7 +637,11 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         ss.lists = my_lists;
         ss.k = a.k;
         ss.cap = a.cap;
-        selection_warp_loop(q, ss, s_ctr + 2 * kSelWarps, lane);
+        ss.rows_f32 = a.rows_f32;
+        ss.q_f32 = a.q_f32 ? a.q_f32 + qbase * a.d : nullptr;
+        ss.d = a.d;
+        ss.id_base = a.id_base;
+        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane);
     }
 
     // ---- final selection: every query's k best of this CTA's point range -> partial[s], by all non-role warps ----
@@ -507,13 +667,16 @@ topk_tc_bytes_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
 }  // namespace tc
 
 cudaError_t tc_set_attributes() {
-    return cudaFuncSetAttribute(tc::topk_tc_bytes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) tc::smem_bytes(tc::kMaxR));
+    const int big = 227 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(tc::topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    return e;
 }
 
-void launch_topk_tc_bytes(const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid, size_t smem,
-                          cudaStream_t st) {
-    tc::topk_tc_bytes_kernel<<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+void launch_topk_tc(bool is_float, const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid,
+                    size_t smem, cudaStream_t st) {
+    if (is_float) tc::topk_tc_kernel<true><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+    else tc::topk_tc_kernel<false><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
 }
 
 }  // namespace gpann

@@ -150,7 +150,11 @@ def test_edge_cases(ctx, gpann_mod, oracle):
         ctx.topk(pts, P[:2], 5, row_range=(10, 100))
     ctx.set_algo(gpann_mod.ALGO_TENSOR)
     with pytest.raises(gpann_mod.GpannError):
-        ctx.topk(pts, P[:2], 5)  # float storage has no byte tensor layout
+        ctx.topk(pts, P[:2], 5, metric=gpann_mod.MIPS)  # the tensor kernels are L2-only: must refuse, not fall back
+    d1, i1, c1 = ctx.topk(pts, P[:3], 5)  # tiny float set through the bf16 tensor path
+    assert ctx.last_algo == "tensor_bf16"
+    d0, i0, _ = oracle.ground_truth(P, P[:3], 5)
+    assert np.array_equal(i1, i0)
     ctx.set_algo(gpann_mod.ALGO_AUTO)
     # id_base shifts reported ids (shard-local -> global)
     p2 = ctx.upload(P, id_base=1000)
@@ -218,3 +222,46 @@ def test_sharded_topk_device_path_matches_single_scan(ctx, gpann_mod, oracle):
     torch.cuda.synchronize()
     d0, i0, _ = oracle.ground_truth(P.astype(np.float32), Q, k)
     assert_topk_exact(dist_out.cpu().numpy(), id_out.cpu().numpy().view(np.uint32), d0, i0)
+
+
+# ---- float data through the bf16 tensor filter + exact fp32 re-rank -----------------------------------------------
+@pytest.mark.parametrize("n,d,nq,k,kind", [(20000, 128, 300, 10, "normal"), (30000, 96, 130, 100, "normal"),
+                                           (50001, 100, 257, 10, "normal"), (8000, 64, 40, 10, "normal"),
+                                           (20000, 128, 100, 10, "offset"), (20000, 96, 100, 10, "unit"),
+                                           (6000, 20, 50, 5, "clustered")])
+def test_tensor_float_vs_oracle(ctx, gpann_mod, oracle, n, d, nq, k, kind):
+    rng = np.random.default_rng(n + d + k)
+    P = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    if kind == "offset":      # far from the origin: worst case for the bf16 filter's error bound (still exact)
+        P += 30.0
+        Q += 30.0
+    elif kind == "unit":      # DEEP-like normalised vectors
+        P /= np.linalg.norm(P, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    elif kind == "clustered":  # queries are perturbed points: tiny distances, strong cancellation
+        Q = P[rng.integers(0, n, nq)] + 1e-3 * rng.standard_normal((nq, d)).astype(np.float32)
+    d1, i1, c1, used = _run(ctx, gpann_mod, P, Q, k, gpann_mod.ALGO_TENSOR, storage=gpann_mod.STORAGE_F32)
+    assert used == "tensor_bf16"
+    d0, i0, c0 = oracle.ground_truth(P, Q, k)
+    assert np.array_equal(c1, c0)
+    assert_topk_close(d1, i1, d0, i0)
+    # the exact re-rank uses the reference's summation order: distances agree to the last bits, not just 1e-5
+    fin = np.isfinite(d0)
+    assert np.abs(d1[fin] - d0[fin]).max() <= 4e-7 * max(1.0, float(d0[fin].max()))
+
+
+def test_tensor_float_matches_stream_kernel_large(ctx, gpann_mod):
+    rng = np.random.default_rng(123)
+    n, d, nq, k = 400_000, 96, 512, 10
+    P = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    pts = ctx.upload(P, storage=gpann_mod.STORAGE_F32)
+    ctx.set_algo(gpann_mod.ALGO_TENSOR)
+    d1, i1, c1 = ctx.topk(pts, Q, k)
+    assert ctx.last_algo == "tensor_bf16"
+    ctx.set_algo(gpann_mod.ALGO_STREAM)
+    d0, i0, c0 = ctx.topk(pts, Q[:64], k)
+    ctx.set_algo(gpann_mod.ALGO_AUTO)
+    assert np.array_equal(i1[:64], i0) and np.array_equal(d1[:64].view(np.uint32), d0.view(np.uint32))
+    assert (np.diff(d1, axis=1) >= 0).all() and all(len(set(r)) == k for r in i1)
