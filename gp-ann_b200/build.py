@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libgpann_cuda.so")
-SOURCES = ["gpann_api.cu", "topk_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
-HEADERS = ["common.cuh", "distance.cuh", "params.h", os.path.join("..", "..", "include", "gpann.h")]
+SOURCES = ["gpann_api.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
+HEADERS = ["common.cuh", "distance.cuh", "params.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "gpann.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

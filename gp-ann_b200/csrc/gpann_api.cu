@@ -44,7 +44,8 @@ struct gpann_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // grow-only scratch, reused across calls (a ctx is externally synchronised)
     DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
-        sort_d, segsums, cent, sums, counts, assign;
+        sort_d, segsums, cent, sums, counts, assign, km_cent, km_hn, km_scal, km_partial, km_amb_list, km_amb_info;
+    int km_mode = 0;     // GPANN_KM_MODE env: 2 = probe (MMA issue only, results invalid)
 };
 
 struct gpann_points {
@@ -67,6 +68,13 @@ struct gpann_points {
     // tensor-path query (t_rows / t_norms / t_ids / tmap above are reused for it)
     int dp = 0;               // padded row length in elements (multiple of 64)
     bool tensor_tried = false;
+    // float storage, d <= 128: split-precision rows for the tensor k-means assignment (kmeans_tc.cu), built lazily
+    unsigned short* km_rows = nullptr;  // [km_npad, 2*km_dpad] bf16: hi block, lo block
+    float* km_xnorm = nullptr;          // [km_npad] |x| rounded up; [km_npad] holds the maximum
+    size_t km_npad = 0;
+    int km_dpad = 0;
+    CUtensorMap km_tmap;
+    bool km_tried = false, km_ok = false;
 };
 
 namespace {
@@ -497,6 +505,122 @@ int topk_host(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t 
     return 0;
 }
 
+// Row-major [rows, row_elems] bf16 matrix fetched as boxes of box_rows x 32 elements (64 bytes), SWIZZLE_64B.
+int encode_rows_map_sw64(gpann_ctx* ctx, CUtensorMap* map, void* base, size_t rows, int row_elems, int box_rows, const char* what) {
+    const cuuint64_t gdim[2] = { (cuuint64_t) row_elems, (cuuint64_t) rows };
+    const cuuint64_t gstride[1] = { (cuuint64_t) row_elems * 2 };
+    const cuuint32_t box[2] = { (cuuint32_t) kmtc::kKBlockElems, (cuuint32_t) box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(ctx, GPANN_E_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int) r));
+    return 0;
+}
+
+// Lazily built by the first tensor-path k-means call over a float point set: split-precision bf16 rows + |x|.
+int build_kmeans_layout(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
+    pts->km_tried = true;
+    const size_t n = pts->n;
+    const int d = (int) pts->d;
+    if (n == 0 || d > 128 || pts->storage != GPANN_STORAGE_F32 || !ctx->encode_tiled || n > 0xFFFFFF00ull) return 0;
+    const int dpad = ((d + 31) / 32) * 32;
+    const size_t n_pad = ((n + kmtc::kTileM - 1) / kmtc::kTileM) * kmtc::kTileM;
+    if (cudaMalloc(&pts->km_rows, n_pad * (size_t) dpad * 4) != cudaSuccess || cudaMalloc(&pts->km_xnorm, (n_pad + 4) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        if (pts->km_rows) cudaFree(pts->km_rows);
+        pts->km_rows = nullptr;
+        return 0;  // not enough memory for the layout: the CUDA-core kernel serves the point set
+    }
+    float* xmax = pts->km_xnorm + n_pad;
+    CU_TRY(ctx, cudaMemsetAsync(xmax, 0, 16, st));
+    launch_split_rows_bf16((const float*) pts->rows, n, d, dpad, n_pad, pts->km_rows, pts->km_xnorm, nullptr, xmax, nullptr,
+                           blocks_for(ctx, n_pad * 32, 256, 32), st);
+    GP_TRY(check_launch(ctx, "split_rows_bf16_kernel"));
+    pts->km_npad = n_pad;
+    pts->km_dpad = dpad;
+    GP_TRY(encode_rows_map_sw64(ctx, &pts->km_tmap, pts->km_rows, n_pad, 2 * dpad, kmtc::kTileM, "k-means points"));
+    pts->km_ok = true;
+    return 0;
+}
+
+// NearestCenters on the tensor cores (kmeans_tc.cu): split-precision filter + exact re-rank of ambiguous points.
+int kmeans_assign_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int32_t* d_assign,
+                         cudaStream_t st) {
+    const int d = (int) pts->d, dpad = pts->km_dpad, nkb = dpad / 32;
+    // shared memory: NB centroids resident (4*dpad bytes each) + a ring of point tiles (128 rows x 4*dpad bytes)
+    int NB = 256, stages = 3;
+    while (kmtc::smem_bytes(NB, nkb, stages) > 225 * 1024) {
+        if (stages > 2) --stages;
+        else if (NB > 128) { NB = 128; stages = 3; }
+        else return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans tensor path: d too large");
+    }
+    if (kc <= 128) NB = 128;
+    const size_t kc_pad = ((kc + NB - 1) / NB) * NB;
+    const int CS = (int) (kc_pad / NB);
+    if (CS > ctx->num_sms) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans tensor path: too many centroids");
+    const size_t n_pad = pts->km_npad;
+    GP_TRY(reserve(ctx, ctx->km_cent, kc_pad * (size_t) dpad * 4));
+    GP_TRY(reserve(ctx, ctx->km_hn, kc_pad * 4));
+    GP_TRY(reserve(ctx, ctx->km_scal, 256));
+    GP_TRY(reserve(ctx, ctx->km_partial, (size_t) CS * n_pad * sizeof(uint4)));
+    GP_TRY(reserve(ctx, ctx->km_amb_list, pts->n * 4));
+    GP_TRY(reserve(ctx, ctx->km_amb_info, pts->n * 8));
+    float* scal = (float*) ctx->km_scal.p;  // [0] cmax, [1] hnmax, [2] ambiguous count, [8..] Consts
+    kmtc::Consts* consts = (kmtc::Consts*) (scal + 8);
+    CU_TRY(ctx, cudaMemsetAsync(scal, 0, 32, st));
+    launch_split_rows_bf16(d_centroids, kc, d, dpad, kc_pad, (unsigned short*) ctx->km_cent.p, nullptr, (float*) ctx->km_hn.p, scal,
+                           scal + 1, blocks_for(ctx, kc_pad * 32, 256, 4), st);
+    GP_TRY(check_launch(ctx, "split_rows_bf16_kernel(centroids)"));
+    launch_kmeans_centroid_consts(pts->km_xnorm + n_pad, scal, scal + 1, (float*) ctx->km_hn.p, (int) kc, (int) kc_pad, consts, st);
+    GP_TRY(check_launch(ctx, "kmeans_centroid_consts_kernel"));
+    CUtensorMap tmap_b;
+    GP_TRY(encode_rows_map_sw64(ctx, &tmap_b, ctx->km_cent.p, kc_pad, 2 * dpad, NB, "k-means centroids"));
+    kmtc::Args a;
+    std::memset(&a, 0, sizeof(a));
+    a.NB = NB;
+    a.CS = CS;
+    a.nkb = nkb;
+    a.nks = (d + 15) / 16;
+    a.stages = stages;
+    a.ntiles = (uint32_t) (n_pad / kmtc::kTileM);
+    a.hnp = (const float*) ctx->km_hn.p;
+    a.partial = (uint4*) ctx->km_partial.p;
+    a.idesc = kmtc::make_idesc_bf16(NB);
+    a.mode = ctx->km_mode;
+    const unsigned groups = (unsigned) std::max<size_t>(1, std::min<size_t>((size_t) (ctx->num_sms / CS), a.ntiles));
+    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+    launch_kmeans_tc(pts->km_tmap, tmap_b, a, groups * CS, kmtc::smem_bytes(NB, nkb, stages), st);
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev1, st);
+        ctx->timed = true;
+    }
+    GP_TRY(check_launch(ctx, "kmeans_tc_kernel"));
+    KmFinalizeParams fp;
+    fp.partial = a.partial;
+    fp.n = pts->n;
+    fp.n_pad = n_pad;
+    fp.CS = CS;
+    fp.NB = NB;
+    fp.kc = (int) kc;
+    fp.d = d;
+    fp.rows = (const float*) pts->rows;
+    fp.centroids = d_centroids;
+    fp.xnorm = pts->km_xnorm;
+    fp.consts = consts;
+    fp.out_assign = d_assign;
+    fp.out_mindist = nullptr;
+    fp.amb_list = (uint32_t*) ctx->km_amb_list.p;
+    fp.amb_count = (uint32_t*) (scal + 2);
+    fp.amb_info = (uint2*) ctx->km_amb_info.p;
+    launch_kmeans_finalize(fp, blocks_for(ctx, pts->n, 256, 8), st);
+    GP_TRY(check_launch(ctx, "kmeans_finalize_kernel"));
+    launch_kmeans_resolve(fp, ctx->num_sms * 8, st);
+    GP_TRY(check_launch(ctx, "kmeans_resolve_kernel"));
+    ctx->last_algo = "kmeans_tensor_bf16x3";
+    return 0;
+}
+
 // ---- k-means helpers -----------------------------------------------------------------------------------------
 RowsView rows_view(const gpann_points* pts) {
     RowsView v;
@@ -510,6 +634,15 @@ RowsView rows_view(const gpann_points* pts) {
 
 int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric,
                          int32_t* d_assign, float* d_mindist, cudaStream_t st) {
+    // tensor path: float rows, L2, d <= 128, no per-point distance requested; AUTO takes it when the contraction is big
+    // enough to pay for the layout (n*kc >= 2^24 and at least 32 centroids)
+    const bool tensor_shape = pts->storage == GPANN_STORAGE_F32 && metric == GPANN_METRIC_L2 && pts->d <= 128 && !d_mindist &&
+                              pts->n > 0;
+    const bool want_tensor = tensor_shape && (ctx->algo == GPANN_ALGO_TENSOR ||
+                                              (ctx->algo == GPANN_ALGO_AUTO && kc >= 32 && pts->n * kc >= ((size_t) 1 << 24)));
+    if (want_tensor && !pts->km_tried) GP_TRY(build_kmeans_layout(ctx, const_cast<gpann_points*>(pts), st));
+    if (want_tensor && pts->km_ok) return kmeans_assign_tensor(ctx, pts, d_centroids, kc, d_assign, st);
+    ctx->last_algo = "kmeans_cuda_core";
     AssignParams p;
     p.pts = rows_view(pts);
     p.centroids = d_centroids;
@@ -612,7 +745,8 @@ int gpann_init(gpann_ctx** out, int device) {
         qres == cudaDriverEntryPointSuccess)
         ctx->encode_tiled = (EncodeTiledFn) fn;
     // opt every large-shared-memory kernel in for this device (function attributes are per device)
-    if (stream_set_attributes() != cudaSuccess || kmeans_set_attributes() != cudaSuccess || tc_set_attributes() != cudaSuccess) {
+    if (stream_set_attributes() != cudaSuccess || kmeans_set_attributes() != cudaSuccess || tc_set_attributes() != cudaSuccess ||
+        kmtc_set_attributes() != cudaSuccess) {
         std::fprintf(stderr, "gpann_init: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -620,6 +754,8 @@ int gpann_init(gpann_ctx** out, int device) {
     }
     const char* mode = std::getenv("GPANN_TC_MODE");
     ctx->tc_mode = mode ? std::atoi(mode) : 0;
+    const char* kmm = std::getenv("GPANN_KM_MODE");
+    ctx->km_mode = kmm ? std::atoi(kmm) : 0;
     const char* pre = std::getenv("GPANN_TC_PREPASS");
     ctx->tc_prepass = pre ? std::atoi(pre) : 1;
     *out = ctx;
@@ -632,7 +768,8 @@ void gpann_destroy(gpann_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
-                       &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign };
+                       &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
+                       &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info };
     for (DevBuf* b : bufs) release(*b);
     cudaStreamDestroy(ctx->stream);
     cudaEventDestroy(ctx->ev0);
@@ -798,6 +935,8 @@ void gpann_points_free(gpann_points* pts) {
     if (pts->t_rows) cudaFree(pts->t_rows);
     if (pts->t_norms) cudaFree(pts->t_norms);
     if (pts->t_ids) cudaFree(pts->t_ids);
+    if (pts->km_rows) cudaFree(pts->km_rows);
+    if (pts->km_xnorm) cudaFree(pts->km_xnorm);
     delete pts;
 }
 size_t gpann_points_n(const gpann_points* pts) { return pts ? pts->n : 0; }

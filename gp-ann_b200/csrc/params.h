@@ -137,6 +137,60 @@ inline uint32_t make_idesc_bf16() {
 }
 }  // namespace tc
 
+// ---- kmeans_tc.cu: split-precision (bf16 hi+lo) tcgen05 nearest-centroid assignment ------------------------------
+namespace kmtc {
+constexpr int kTileM = 128;       // points per tile (UMMA M, TMEM lanes)
+constexpr int kKBlockElems = 32;  // bf16 elements per K block = one SWIZZLE_64B row (64 bytes)
+constexpr int kMaxStages = 3;
+constexpr int kFilterWarps = 8;   // 4 TMEM lane quadrants x 2 column halves
+constexpr int kThreads = 64 + 32 * kFilterWarps;
+constexpr int kABlockBytes = kTileM * 64;  // 8 KB per K block of a point tile
+
+// Per-round constants computed on the device by kmeans_centroid_consts_kernel (no host round trip).
+struct Consts {
+    float offset;   // added to every score so that scores are non-negative floats (integer-comparable)
+    float cmax;     // max centroid norm |c| (rounded up)
+    float xmax;     // max point norm |x| (rounded up), copied from the point layout
+    float eps;      // relative error bound of the split-precision dot product: |dot~ - dot| <= eps*|x|*|c|
+};
+
+struct Args {
+    int NB;                  // centroids per CTA (UMMA N): 128 or 256
+    int CS;                  // centroid splits = kc_pad / NB
+    int nkb;                 // 32-element K blocks per term (dpad / 32); a row holds 2*nkb blocks: hi then lo
+    int nks;                 // K steps (16 elements) per term = ceil(d / 16)
+    int stages;              // depth of the point-tile ring
+    uint32_t ntiles;         // point tiles of 128 rows
+    const float* hnp;        // [kc_pad] 0.5*|c|^2 - offset (0 for padding centroids)
+    uint4* partial;          // [CS][ntiles*128] per point: top-3 packed scores + chunk ids
+    uint32_t idesc;
+    int mode;                // 0 = full; 2 = probe: MMA issue only (results invalid)
+};
+
+inline size_t smem_bytes(int NB, int nkb, int stages) {
+    return 1024 + (size_t) 2 * nkb * NB * 64 /*centroids*/ + (size_t) stages * 2 * nkb * kABlockBytes /*point tiles*/ +
+           256 /*barriers*/ + (size_t) NB * 4 /*hn'*/ + (size_t) 2 * kTileM * 16 /*half-merge buffers*/;
+}
+inline uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (kTileM >> 4) << 24);
+}
+}  // namespace kmtc
+
+struct KmFinalizeParams {
+    const uint4* partial;    // [CS][n_pad]
+    size_t n, n_pad;
+    int CS, NB, kc, d;
+    const float* rows;       // [n, d] original fp32 point rows
+    const float* centroids;  // [kc, d] fp32
+    const float* xnorm;      // [n_pad] |x| (rounded up)
+    const kmtc::Consts* consts;
+    int32_t* out_assign;
+    float* out_mindist;      // optional
+    uint32_t* amb_list;      // [n] ambiguous point rows (mode in the top 2 bits)
+    uint32_t* amb_count;
+    uint2* amb_info;         // [n] candidates of an ambiguous point: {j1, j2 | mode << 30}
+};
+
 // ---- launchers (each defined in the translation unit that owns the kernel) -------------------------------------
 cudaError_t stream_set_attributes();
 cudaError_t kmeans_set_attributes();
@@ -173,6 +227,17 @@ void launch_gather_sorted_rows_bf16(const float* rows, size_t n, int d, int dp, 
                                     int blocks, cudaStream_t st);
 void launch_prep_queries_bf16(const float* q, int nq, int d, int dp, int nq_pad, unsigned short* out_rows, float* out_norms,
                               float* out_q_f32, uint32_t* bound, cudaStream_t st);
+
+// kmeans_tc.cu
+cudaError_t kmtc_set_attributes();
+void launch_split_rows_bf16(const float* rows, size_t n, int d, int dpad, size_t n_pad, unsigned short* out_rows, float* out_norm,
+                            float* out_hn, float* max_norm, float* max_hn, int blocks, cudaStream_t st);
+void launch_kmeans_centroid_consts(const float* xmax, const float* cmax, const float* hnmax, float* hn, int kc, int kc_pad,
+                                   kmtc::Consts* consts, cudaStream_t st);
+void launch_kmeans_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const kmtc::Args& a, unsigned grid, size_t smem,
+                      cudaStream_t st);
+void launch_kmeans_finalize(const KmFinalizeParams& p, int blocks, cudaStream_t st);
+void launch_kmeans_resolve(const KmFinalizeParams& p, int blocks, cudaStream_t st);
 
 void launch_topk_tc(bool is_float, const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid,
                     size_t smem, cudaStream_t st);

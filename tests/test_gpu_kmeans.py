@@ -107,3 +107,60 @@ def test_sharded_kmeans_round_matches_unsharded(ctx, oracle):
     c0, s0 = oracle.aggregate(P, a0, kc, normalize=False)
     assert np.array_equal(counts.cpu().numpy(), s0.astype(np.int64))
     np.testing.assert_allclose(sums.cpu().numpy(), c0, rtol=1e-5, atol=1e-4)
+
+
+# ---- tensor-core assignment (kmeans_tc.cu): split-precision filter + exact re-rank must equal the CPU scan ------------
+@pytest.fixture
+def tensor_ctx(ctx, gpann_mod):
+    ctx.set_algo(gpann_mod.ALGO_TENSOR)
+    yield ctx
+    ctx.set_algo(gpann_mod.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("n,d,kc,kind", [
+    (20000, 96, 1024, "mixture"), (5001, 100, 300, "mixture"), (3000, 32, 1, "normal"), (777, 20, 1024, "normal"),
+    (40000, 128, 256, "normal"), (10000, 17, 37, "mixture"), (9000, 64, 129, "offset"), (6000, 96, 513, "normal"),
+])
+def test_tensor_assign_matches_oracle(tensor_ctx, oracle, n, d, kc, kind):
+    rng = np.random.default_rng(n + kc)
+    if kind == "mixture":
+        P = _mixture(rng, n, d, max(2, kc // 3))  # several centroids fall into the same component: near ties
+    elif kind == "offset":
+        P = (rng.standard_normal((n, d)) + 50.0).astype(np.float32)  # large norms relative to the distances
+    else:
+        P = rng.standard_normal((n, d)).astype(np.float32)
+    C = P[rng.choice(n, kc, replace=False)].copy() if kc <= n else rng.standard_normal((kc, d)).astype(np.float32)
+    pts = tensor_ctx.upload(P)
+    a1 = tensor_ctx.kmeans_assign(pts, C)
+    assert tensor_ctx.last_algo == "kmeans_tensor_bf16x3", tensor_ctx.last_algo
+    a0, _ = oracle.nearest_centers(P, C)
+    assert np.array_equal(a1, a0), f"{(a1 != a0).sum()} of {n} assignments differ"
+
+
+def test_tensor_assign_exact_ties(tensor_ctx, oracle):
+    """Duplicated centroids and points that coincide with centroids: the lower index must win (strict <, kmeans.cpp:18)."""
+    rng = np.random.default_rng(5)
+    P = rng.integers(0, 4, (8000, 48)).astype(np.float32)
+    C = np.concatenate([P[:150], P[:150], P[100:250]])
+    a1 = tensor_ctx.kmeans_assign(tensor_ctx.upload(P, storage=1), C)
+    assert tensor_ctx.last_algo == "kmeans_tensor_bf16x3"
+    a0, _ = oracle.nearest_centers(P, C)
+    assert np.array_equal(a1, a0)
+
+
+def test_tensor_step_matches_cuda_core_step(ctx, gpann_mod, oracle):
+    rng = np.random.default_rng(21)
+    n, d, kc = 60000, 96, 512
+    P = _mixture(rng, n, d, 200)
+    C = P[rng.choice(n, kc, replace=False)].copy()
+    pts = ctx.upload(P)
+    ctx.set_algo(gpann_mod.ALGO_STREAM)
+    a0, c0, s0 = ctx.kmeans_step(pts, C)
+    assert ctx.last_algo == "kmeans_cuda_core"
+    ctx.set_algo(gpann_mod.ALGO_AUTO)  # n*kc >= 2^24: AUTO takes the tensor path
+    a1, c1, s1 = ctx.kmeans_step(pts, C)
+    assert ctx.last_algo == "kmeans_tensor_bf16x3"
+    assert np.array_equal(a1, a0) and np.array_equal(s1, s0)
+    assert np.array_equal(c1.view(np.uint32), c0.view(np.uint32))  # same assignment -> same fixed-order sums
+    a_or, _ = oracle.nearest_centers(P, C)
+    assert np.array_equal(a1, a_or)
