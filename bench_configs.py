@@ -128,7 +128,10 @@ def main():
             "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flop / (ms * 1e-3) / 1e12 / peak, "peak_source": f"bf16_tflops_sustained ({pk_src})",
                          "note": "whole round (assignment + sums), not the assignment kernel alone"},
-            "hbm_gbs": n * d * 4 * 2 / (ms * 1e-3) / 1e9}
+            "hbm_gbs": n * d * 4 * 2 / (ms * 1e-3) / 1e9, "ambiguous_points": ctx.last_ambiguous}
+    ctx.set_timing(True)
+    round_()
+    line["assign_kernel_ms"] = ctx.last_kernel_ms()
     print(json.dumps(line), flush=True)
 
 

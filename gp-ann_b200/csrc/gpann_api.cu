@@ -46,6 +46,10 @@ struct gpann_ctx {
     DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
         sort_d, segsums, cent, sums, counts, assign, km_cent, km_hn, km_scal, km_partial, km_amb_list, km_amb_info;
     int km_mode = 0;     // GPANN_KM_MODE env: 2 = probe (MMA issue only, results invalid)
+    // streaming entry points: second stream for the H2D copies, double-buffered raw chunks, one chunk layout
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
+    DevBuf st_raw[2], st_rows, st_norms, st_ids, st_a, st_b, st_c, st_d, st_tmp;
 };
 
 struct gpann_points {
@@ -329,117 +333,263 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     return launch_merge(ctx, p.partial, gx, nq, nq, k, out, 0, st);
 }
 
-// The tcgen05 path: byte storage (exact int32 distances) or float storage (bf16 filter + exact fp32 re-rank).
-// *queries_ok_host = 0 (and nothing written) when byte points meet queries that are not integer-valued in the
-// storage's range; the caller then takes the exact float scan.
+// ---- the tcgen05 path: byte storage (exact int32 distances) or float storage (bf16 filter + exact fp32 re-rank) ----
+// A scan is split into query preparation (once per query batch) and the scan of one norm-sorted layout, so the
+// streaming entry points can reuse the prepared queries for every chunk of a host-resident point set.
+struct TcLayout {                 // one norm-sorted tensor layout: a whole point set or one streamed chunk
+    const CUtensorMap* tmap;
+    const void* norms;
+    const uint32_t* ids;
+    size_t n_pad;
+    const float* rows_f32;        // float path: original rows for the exact re-rank (ids - id_base index them)
+    uint32_t id_base;
+};
+
+struct TcPlan {
+    bool is_float = false;
+    int is_signed = 0, d = 0, dp = 0, kblocks = 1, max_r = tc::kMaxR, stages = 3, qcap = 1024;
+    int R = 1, G = 1, k = 0, cap = 128;
+    size_t nqb = 0, nq_pad = 0;
+    CUtensorMap tmap_q;
+};
+
+size_t tc_batch_max(const gpann_ctx* ctx, int kblocks) { return (size_t) ctx->num_sms * (kblocks == 1 ? tc::kMaxR : 2) * tc::kTileM; }
+
+// Prepare one batch of nqb <= tc_batch_max queries.  *ok = 0 (and nothing else done) when byte points meet queries
+// that are not integer-valued in the storage's range; the caller then takes the exact float scan.
+int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, const float* dq, size_t nqb, int k, cudaStream_t st,
+                       int* ok) {
+    pl.is_float = storage == GPANN_STORAGE_F32;
+    pl.is_signed = storage == GPANN_STORAGE_S8;
+    pl.d = d;
+    pl.dp = dp;
+    pl.kblocks = pl.is_float ? dp / 64 : 1;
+    // shared-memory plan: bytes / one K block: 4 Q tiles, 3 stages, 1024-deep queues; two K blocks: 2, 2, 512
+    pl.max_r = pl.kblocks == 1 ? tc::kMaxR : 2;
+    pl.stages = pl.kblocks == 1 ? 3 : 2;
+    pl.qcap = pl.kblocks == 1 ? 1024 : 512;
+    pl.nqb = nqb;
+    pl.k = k;
+    pl.R = (int) std::min<size_t>(pl.max_r, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
+    pl.G = (int) ((nqb + (size_t) pl.R * tc::kTileM - 1) / ((size_t) pl.R * tc::kTileM));
+    pl.nq_pad = (size_t) pl.G * pl.R * tc::kTileM;
+    pl.cap = std::max(128, pow2_ceil(k + 64));
+    *ok = 1;
+    const size_t qrow_bytes = pl.is_float ? (size_t) dp * 2 : tc::kRowBytes;
+    GP_TRY(reserve(ctx, ctx->qrows, pl.nq_pad * qrow_bytes));
+    GP_TRY(reserve(ctx, ctx->qnorm, pl.nq_pad * 4));
+    GP_TRY(reserve(ctx, ctx->bound, pl.nq_pad * 4));
+    GP_TRY(reserve(ctx, ctx->flags, 64));
+    if (pl.is_float) {
+        GP_TRY(reserve(ctx, ctx->qf32, pl.nq_pad * d * sizeof(float)));
+        launch_prep_queries_bf16(dq, (int) nqb, d, dp, (int) pl.nq_pad, (unsigned short*) ctx->qrows.p, (float*) ctx->qnorm.p,
+                                 (float*) ctx->qf32.p, (uint32_t*) ctx->bound.p, st);
+        GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
+    } else {
+        int one = 1;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
+        launch_prep_queries_bytes(dq, (int) nqb, d, (int) pl.nq_pad, pl.is_signed, (unsigned char*) ctx->qrows.p,
+                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
+        GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
+        int okh = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&okh, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        if (!okh) {
+            *ok = 0;
+            return 0;
+        }
+    }
+    return encode_rows_map(ctx, &pl.tmap_q, ctx->qrows.p, pl.nq_pad, tc::kTileM, "queries", pl.is_float,
+                           pl.is_float ? dp : tc::kRowBytes);
+}
+
+// Scan one layout for the prepared batch.  The per-split partial lists land in ctx->partial [1 + S, nq_pad, k] (parts
+// 1..S); with `carry` part 0 holds the running result of earlier chunks (and receives the merged one, together with
+// the tightened per-query bounds); otherwise the merged result of the S parts goes to `out` at query offset q_off.
+int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass, bool carry, bool carry_init, const TopkOut& out,
+            size_t q_off, cudaStream_t st) {
+    const int k = pl.k;
+    const uint32_t tiles_total = (uint32_t) (lay.n_pad / tc::kTileN);
+    const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / pl.G), tiles_total));
+    const int S_max = std::max(1, ctx->num_sms / pl.G);
+    const size_t part_keys = pl.nq_pad * (size_t) k;
+    GP_TRY(reserve(ctx, ctx->cand, (size_t) pl.G * S * pl.R * tc::kTileM * pl.cap * sizeof(uint64_t)));
+    GP_TRY(reserve(ctx, ctx->partial, (size_t) (S_max + 1) * part_keys * sizeof(uint64_t)));
+    uint64_t* carry_keys = (uint64_t*) ctx->partial.p;  // part 0: the running result; the splits write parts 1..S
+    uint64_t* partial = carry_keys + part_keys;
+    if (carry && carry_init) CU_TRY(ctx, cudaMemsetAsync(carry_keys, 0xFF, part_keys * sizeof(uint64_t), st));
+    tc::Args a;
+    std::memset(&a, 0, sizeof(a));
+    a.pnorm = lay.norms;
+    a.pid = lay.ids;
+    a.qnorm = ctx->qnorm.p;
+    a.R = pl.R;
+    a.G = pl.G;
+    a.S = S;
+    a.nks = pl.is_float ? (pl.d + 15) / 16 : (pl.d + 31) / 32;
+    a.kblocks = pl.kblocks;
+    a.stages = pl.stages;
+    a.qcap = pl.qcap;
+    a.k = k;
+    a.cap = pl.cap;
+    a.idesc = pl.is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(pl.is_signed);
+    a.cand = (uint64_t*) ctx->cand.p;
+    a.partial = partial;
+    a.bound = (uint32_t*) ctx->bound.p;
+    a.mode = ctx->tc_mode;
+    a.rows_f32 = pl.is_float ? lay.rows_f32 : nullptr;
+    a.q_f32 = pl.is_float ? (const float*) ctx->qf32.p : nullptr;
+    a.d = pl.d;
+    a.id_base = lay.id_base;
+    a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
+    const unsigned grid = (unsigned) (pl.G * S);
+    const size_t smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap);
+    // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
+    // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
+    // (a cold start pushes EVERY distance through the selection warps).  Two levels: 1 tile per split (cold, but
+    // tiny), then 12 tiles per split filtered by the level-1 bound.
+    if (prepass && ctx->tc_prepass && ctx->tc_mode == 0) {
+        const uint32_t levels[2] = { 1, 12 };
+        for (uint32_t per_split : levels) {
+            const uint32_t nsample = (uint32_t) S * per_split;
+            if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
+            a.ntiles = nsample;
+            a.tile_stride = tiles_total / nsample;
+            a.tile_lo = a.tile_stride / 2;
+            launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
+            GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
+            TopkOut b;
+            b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
+            b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
+            GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st));
+        }
+    }
+    a.tile_lo = 0;
+    a.tile_stride = 1;
+    a.ntiles = tiles_total;
+    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
+    launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
+    if (ctx->timing) {
+        cudaEventRecord(ctx->ev1, st);
+        ctx->timed = true;
+    }
+    GP_TRY(check_launch(ctx, "topk_tc_kernel"));
+    if (!carry) return launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, out, q_off, st);
+    TopkOut c;
+    c.keys = carry_keys;              // in place: a warp reads all parts of its query before it writes
+    c.kth = (float*) ctx->bound.p;
+    c.kth_full_only = 1;
+    return launch_merge(ctx, carry_keys, S + 1, pl.nq_pad, pl.nqb, k, c, 0, st);
+}
+
 int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
                 cudaStream_t st, int* queries_ok_host) {
     const bool is_float = pts->storage == GPANN_STORAGE_F32;
-    const int is_signed = pts->storage == GPANN_STORAGE_S8;
     const int d = (int) pts->d;
-    const int kblocks = is_float ? pts->dp / 64 : 1;
-    // shared-memory plan: bytes / one K block: 4 Q tiles, 3 stages, 1024-deep queues; two K blocks: 2, 2, 512
-    const int max_r = kblocks == 1 ? tc::kMaxR : 2;
-    const int stages = kblocks == 1 ? 3 : 2;
-    const int qcap = kblocks == 1 ? 1024 : 512;
-    const size_t batch_max = (size_t) ctx->num_sms * max_r * tc::kTileM;
+    const size_t batch_max = tc_batch_max(ctx, is_float ? pts->dp / 64 : 1);
+    TcLayout lay;
+    lay.tmap = &pts->tmap;
+    lay.norms = pts->t_norms;
+    lay.ids = pts->t_ids;
+    lay.n_pad = pts->n_pad;
+    lay.rows_f32 = is_float ? (const float*) pts->rows : nullptr;
+    lay.id_base = pts->id_base;
     *queries_ok_host = 1;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
-        const size_t nqb = std::min(batch_max, nq - q0);
-        const int R = (int) std::min<size_t>(max_r, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
-        const int G = (int) ((nqb + (size_t) R * tc::kTileM - 1) / ((size_t) R * tc::kTileM));
-        const uint32_t tiles_total = (uint32_t) (pts->n_pad / tc::kTileN);
-        const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / G), tiles_total));
-        const size_t nq_pad = (size_t) G * R * tc::kTileM;
-        const int cap = std::max(128, pow2_ceil(k + 64));
-        const size_t qrow_bytes = is_float ? (size_t) pts->dp * 2 : tc::kRowBytes;
-        GP_TRY(reserve(ctx, ctx->qrows, nq_pad * qrow_bytes));
-        GP_TRY(reserve(ctx, ctx->qnorm, nq_pad * 4));
-        GP_TRY(reserve(ctx, ctx->bound, nq_pad * 4));
-        GP_TRY(reserve(ctx, ctx->flags, 64));
-        GP_TRY(reserve(ctx, ctx->cand, (size_t) G * S * R * tc::kTileM * cap * sizeof(uint64_t)));
-        GP_TRY(reserve(ctx, ctx->partial, (size_t) S * nq_pad * k * sizeof(uint64_t)));
-        if (is_float) {
-            GP_TRY(reserve(ctx, ctx->qf32, nq_pad * d * sizeof(float)));
-            launch_prep_queries_bf16(dq + q0 * d, (int) nqb, d, pts->dp, (int) nq_pad, (unsigned short*) ctx->qrows.p,
-                                     (float*) ctx->qnorm.p, (float*) ctx->qf32.p, (uint32_t*) ctx->bound.p, st);
-            GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
-        } else {
-            int one = 1;
-            CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
-            launch_prep_queries_bytes(dq + q0 * d, (int) nqb, d, (int) nq_pad, is_signed, (unsigned char*) ctx->qrows.p,
-                                      (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
-            GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
-            int ok = 0;
-            CU_TRY(ctx, cudaMemcpyAsync(&ok, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
-            CU_TRY(ctx, cudaStreamSynchronize(st));
-            if (!ok) {
-                *queries_ok_host = 0;
-                return 0;
-            }
+        TcPlan pl;
+        int ok = 1;
+        GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st, &ok));
+        if (!ok) {
+            *queries_ok_host = 0;
+            return 0;
         }
-        CUtensorMap tmap_q;
-        GP_TRY(encode_rows_map(ctx, &tmap_q, ctx->qrows.p, nq_pad, tc::kTileM, "queries", is_float, is_float ? pts->dp : tc::kRowBytes));
-        tc::Args a;
-        std::memset(&a, 0, sizeof(a));
-        a.pnorm = pts->t_norms;
-        a.pid = pts->t_ids;
-        a.qnorm = ctx->qnorm.p;
-        a.R = R;
-        a.G = G;
-        a.S = S;
-        a.nks = is_float ? (d + 15) / 16 : (d + 31) / 32;
-        a.kblocks = kblocks;
-        a.stages = stages;
-        a.qcap = qcap;
-        a.k = k;
-        a.cap = cap;
-        a.idesc = is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(is_signed);
-        a.cand = (uint64_t*) ctx->cand.p;
-        a.partial = (uint64_t*) ctx->partial.p;
-        a.bound = (uint32_t*) ctx->bound.p;
-        a.mode = ctx->tc_mode;
-        a.rows_f32 = is_float ? (const float*) pts->rows : nullptr;
-        a.q_f32 = is_float ? (const float*) ctx->qf32.p : nullptr;
-        a.d = d;
-        a.id_base = pts->id_base;
-        a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
-        const unsigned grid = (unsigned) (G * S);
-        const size_t smem = tc::smem_bytes(R, kblocks, stages, qcap);
-        // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
-        // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
-        // (a cold start pushes EVERY distance through the selection warps).  Two levels: 1 tile per split (cold, but
-        // tiny), then 12 tiles per split filtered by the level-1 bound.
-        if (ctx->tc_prepass && ctx->tc_mode == 0) {
-            const uint32_t levels[2] = { 1, 12 };
-            for (uint32_t per_split : levels) {
-                const uint32_t nsample = (uint32_t) S * per_split;
-                if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
-                a.ntiles = nsample;
-                a.tile_stride = tiles_total / nsample;
-                a.tile_lo = a.tile_stride / 2;
-                launch_topk_tc(is_float, pts->tmap, tmap_q, a, grid, smem, st);
-                GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
-                TopkOut b;
-                b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
-                b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
-                GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, b, 0, st));
-            }
-        }
-        a.tile_lo = 0;
-        a.tile_stride = 1;
-        a.ntiles = tiles_total;
-        if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-        launch_topk_tc(is_float, pts->tmap, tmap_q, a, grid, smem, st);
-        if (ctx->timing) {
-            cudaEventRecord(ctx->ev1, st);
-            ctx->timed = true;
-        }
-        GP_TRY(check_launch(ctx, "topk_tc_kernel"));
-        GP_TRY(launch_merge(ctx, a.partial, S, nq_pad, nqb, k, out, q0, st));
+        GP_TRY(tc_scan(ctx, pl, lay, true, false, false, out, q0, st));
     }
-    ctx->last_algo = is_float ? "tensor_bf16" : (is_signed ? "tensor_s8" : "tensor_u8");
+    ctx->last_algo = is_float ? "tensor_bf16" : (pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8");
     return 0;
+}
+
+// ---- streamed scan of a HOST-resident byte point set -----------------------------------------------------------
+// The set never sits in HBM as a whole: chunks of `chunk_rows` rows go H2D on a second stream into one of two raw
+// buffers while the previous chunk is turned into a norm-sorted layout and scanned; the running top-k and the per-query
+// bounds carry from chunk to chunk (tc_scan's carry part), so every chunk after the first starts with a tight filter.
+int topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base, const float* dq,
+                      size_t nq, int k, size_t chunk_rows, const TopkOut& out, cudaStream_t st) {
+    if (d == 0 || d > (size_t) tc::kRowBytes) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: d must be in [1,128]");
+    if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream: k must be in [1,448]");
+    if ((uint64_t) id_base + n > 0xFFFFFFFFull) return fail(ctx, GPANN_E_ARG, "topk_stream: ids exceed 32 bits (recall.h:30)");
+    if (nq == 0) return 0;
+    if (nq > tc_batch_max(ctx, 1)) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: too many queries for one batch");
+    if (!ctx->encode_tiled) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: cuTensorMapEncodeTiled unavailable");
+    if (!ctx->copy_stream) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t tile = tc::kTileN;
+    size_t C = chunk_rows ? chunk_rows : ((size_t) 4 << 20);
+    C = std::min(((C + tile - 1) / tile) * tile, ((std::max<size_t>(n, 1) + tile - 1) / tile) * tile);
+    const size_t nchunks = std::max<size_t>(1, (n + C - 1) / C);
+    for (int b = 0; b < 2; ++b) GP_TRY(reserve(ctx, ctx->st_raw[b], C * d));
+    GP_TRY(reserve(ctx, ctx->st_rows, C * tc::kRowBytes));
+    GP_TRY(reserve(ctx, ctx->st_norms, C * 4));
+    GP_TRY(reserve(ctx, ctx->st_ids, C * 4));
+    GP_TRY(reserve(ctx, ctx->st_a, C * 4));
+    GP_TRY(reserve(ctx, ctx->st_b, C * 4));
+    GP_TRY(reserve(ctx, ctx->st_c, C * 4));
+    GP_TRY(reserve(ctx, ctx->st_d, C * 4));
+    size_t tmp_bytes = 0;
+    sort_pairs_u32(nullptr, tmp_bytes, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_b.p, (uint32_t*) ctx->st_c.p,
+                   (uint32_t*) ctx->st_d.p, C, 25, st);
+    GP_TRY(reserve(ctx, ctx->st_tmp, tmp_bytes));
+    TcPlan pl;
+    int ok = 1;
+    GP_TRY(tc_prepare_queries(ctx, pl, is_signed ? GPANN_STORAGE_S8 : GPANN_STORAGE_U8, (int) d, 0, dq, nq, k, st, &ok));
+    if (!ok) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: queries are not integer-valued in the storage range");
+    CUtensorMap tmap;
+    GP_TRY(encode_rows_map(ctx, &tmap, ctx->st_rows.p, C, tc::kTileN, "chunk"));
+    TcLayout lay;
+    lay.tmap = &tmap;
+    lay.norms = ctx->st_norms.p;
+    lay.ids = (const uint32_t*) ctx->st_ids.p;
+    lay.rows_f32 = nullptr;
+    const char* src = (const char*) host_rows;
+    bool timed_any = false;
+    for (size_t c = 0; c < nchunks; ++c) {
+        const int b = (int) (c & 1);
+        const size_t r0 = c * C, rows_c = std::min(C, n - std::min(n, r0));
+        const size_t n_pad = std::max(tile, ((rows_c + tile - 1) / tile) * tile);
+        unsigned char* raw = (unsigned char*) ctx->st_raw[b].p;
+        // raw[b] is free once the gather of the chunk that used it last (this or an earlier call) is done
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+        if (rows_c) CU_TRY(ctx, cudaMemcpyAsync(raw, src + r0 * d, rows_c * d, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
+        if (rows_c) {
+            launch_byte_norms(raw, rows_c, (int) d, d, is_signed, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_c.p,
+                              blocks_for(ctx, rows_c), st);
+            GP_TRY(check_launch(ctx, "byte_norms_kernel"));
+            size_t tb = ctx->st_tmp.cap;
+            if (sort_pairs_u32(ctx->st_tmp.p, tb, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_b.p, (uint32_t*) ctx->st_c.p,
+                               (uint32_t*) ctx->st_d.p, rows_c, 25, st) != cudaSuccess)
+                return fail(ctx, GPANN_E_CUDA, "topk_stream: radix sort failed");
+            ctx->launches += 4;
+        }
+        launch_gather_sorted_rows(raw, rows_c, (int) d, d, (const uint32_t*) ctx->st_d.p, (const uint32_t*) ctx->st_b.p,
+                                  id_base + (uint32_t) r0, n_pad, (unsigned char*) ctx->st_rows.p, (int32_t*) ctx->st_norms.p,
+                                  (uint32_t*) ctx->st_ids.p, blocks_for(ctx, n_pad * 32, 256, 32), st);
+        GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], st));
+        lay.n_pad = n_pad;
+        lay.id_base = id_base + (uint32_t) r0;
+        GP_TRY(tc_scan(ctx, pl, lay, c == 0, true, c == 0, out, 0, st));
+        timed_any = true;
+    }
+    (void) timed_any;
+    ctx->last_algo = is_signed ? "tensor_s8_stream" : "tensor_u8_stream";
+    return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, pl.nq_pad, nq, k, out, 0, st);
 }
 
 int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
@@ -771,6 +921,14 @@ void gpann_destroy(gpann_ctx* ctx) {
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
                        &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info };
     for (DevBuf* b : bufs) release(*b);
+    DevBuf* sbufs[] = { &ctx->st_raw[0], &ctx->st_raw[1], &ctx->st_rows, &ctx->st_norms, &ctx->st_ids, &ctx->st_a, &ctx->st_b,
+                        &ctx->st_c, &ctx->st_d, &ctx->st_tmp };
+    for (DevBuf* b : sbufs) release(*b);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    }
     cudaStreamDestroy(ctx->stream);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -798,6 +956,14 @@ float gpann_last_kernel_ms(gpann_ctx* ctx) {
     return ms;
 }
 const char* gpann_last_algo(const gpann_ctx* ctx) { return ctx ? ctx->last_algo : "none"; }
+uint64_t gpann_last_ambiguous(gpann_ctx* ctx) {
+    if (!ctx || !ctx->km_scal.p) return 0;
+    uint32_t v = 0;
+    cudaSetDevice(ctx->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+    if (cudaMemcpy(&v, (const float*) ctx->km_scal.p + 2, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return v;
+}
 
 static int finish_points(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st, gpann_points** out) {
     if (pts->storage != GPANN_STORAGE_F32) {
@@ -962,6 +1128,43 @@ int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, 
     if (!ctx) return GPANN_E_ARG;
     if (!pts) return fail(ctx, GPANN_E_ARG, "topk_range: null point set");
     return topk_host(ctx, pts, row_begin, row_end, queries, nq, k, metric, out_dist, out_id, out_count, nullptr);
+}
+
+int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                            const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
+                            uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if ((!host_rows && n) || !queries) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes: null argument");
+    if (nq == 0) return 0;
+    if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes: k must be in [1,448]");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
+    GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->id_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->cnt_out, nq * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdev.p, queries, nq * d * 4, cudaMemcpyHostToDevice, st));
+    TopkOut o;
+    o.dist = out_dist ? (float*) ctx->dist_out.p : nullptr;
+    o.id = out_id ? (uint32_t*) ctx->id_out.p : nullptr;
+    o.count = out_count ? (uint32_t*) ctx->cnt_out.p : nullptr;
+    GP_TRY(topk_stream_bytes(ctx, host_rows, n, d, is_signed, id_base, (const float*) ctx->qdev.p, nq, k, chunk_rows, o, st));
+    if (out_dist) CU_TRY(ctx, cudaMemcpyAsync(out_dist, o.dist, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_id) CU_TRY(ctx, cudaMemcpyAsync(out_id, o.id, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_count) CU_TRY(ctx, cudaMemcpyAsync(out_count, o.count, nq * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                                   const float* dev_queries, size_t nq, int k, size_t chunk_rows, uint64_t* dev_out_keys,
+                                   void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if ((!host_rows && n) || !dev_queries || !dev_out_keys) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes_device: null argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    TopkOut o;
+    o.keys = dev_out_keys;
+    return topk_stream_bytes(ctx, host_rows, n, d, is_signed, id_base, dev_queries, nq, k, chunk_rows, o, (cudaStream_t) stream);
 }
 
 int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,

@@ -24,6 +24,7 @@ SYMBOLS = {
     "gpann_last_algo": (C.c_char_p, [_vp]),
     "gpann_set_timing": (_i, [_vp, _i]),
     "gpann_last_kernel_ms": (C.c_float, [_vp]),
+    "gpann_last_ambiguous": (_u64, [_vp]),
     "gpann_points_upload": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
     "gpann_points_upload_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, C.POINTER(_vp)]),
     "gpann_points_from_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, C.POINTER(_vp)]),
@@ -34,6 +35,8 @@ SYMBOLS = {
     "gpann_topk": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "gpann_kth_distance": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "gpann_topk_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "gpann_topk_stream_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp]),
+    "gpann_topk_stream_bytes_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp]),
     "gpann_topk_range": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "gpann_merge_keys_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
     "gpann_pack_key": (_u64, [C.c_float, _u32]),
@@ -138,6 +141,11 @@ class Context:
         return float(self.lib.gpann_last_kernel_ms(self.h))
 
     @property
+    def last_ambiguous(self):
+        """Points the last tensor-path k-means assignment had to re-rank exactly (diagnostic)."""
+        return int(self.lib.gpann_last_ambiguous(self.h))
+
+    @property
     def launch_count(self):
         return int(self.lib.gpann_launch_count(self.h))
 
@@ -183,6 +191,23 @@ class Context:
                                            _ptr(ids), _ptr(cnt))
         self.check(rc)
         return dist, ids, cnt
+
+    def topk_stream_bytes(self, host_rows, queries, k, id_base=0, chunk_rows=0):
+        """Exact top-k against a host-resident uint8/int8 array streamed through the device in chunks."""
+        rows = np.ascontiguousarray(host_rows)
+        assert rows.dtype in (np.uint8, np.int8)
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        dist, ids, cnt = np.empty((nq, k), np.float32), np.empty((nq, k), np.uint32), np.empty(nq, np.uint32)
+        self.check(self.lib.gpann_topk_stream_bytes(self.h, _ptr(rows), rows.shape[0], rows.shape[1], int(rows.dtype == np.int8),
+                                                    id_base, _ptr(q), nq, k, chunk_rows, _ptr(dist), _ptr(ids), _ptr(cnt)))
+        return dist, ids, cnt
+
+    def topk_stream_bytes_device(self, host_ptr, n, d, is_signed, dev_queries, nq, k, dev_out_keys, id_base=0, chunk_rows=0,
+                                 stream=None):
+        self.check(self.lib.gpann_topk_stream_bytes_device(self.h, C.c_void_p(host_ptr), n, d, int(is_signed), id_base,
+                                                           C.c_void_p(dev_queries), nq, k, chunk_rows, C.c_void_p(dev_out_keys),
+                                                           C.c_void_p(stream or 0)))
 
     def kth_distance(self, pts, queries, k, metric=L2):
         q = np.ascontiguousarray(queries, dtype=np.float32)

@@ -62,6 +62,9 @@ const char* gpann_last_algo(const gpann_ctx* ctx);
  * last bracket and returns its duration in milliseconds (negative if none was recorded). */
 int gpann_set_timing(gpann_ctx* ctx, int on);
 float gpann_last_kernel_ms(gpann_ctx* ctx);
+/* Diagnostic: number of points of the last tensor-path k-means assignment whose winner the split-precision filter could
+ * not certify and that were re-ranked exactly in fp32 (waits for the stream the call ran on; 0 if none ran). */
+uint64_t gpann_last_ambiguous(gpann_ctx* ctx);
 
 /* ---- point sets: replaces PointSet (src/defs.h:10-21) as the scanned operand --------------------------- */
 /* Upload n rows of d floats (row-major, as PointSet::coordinates).  Ids reported by gpann_topk are
@@ -90,6 +93,21 @@ int gpann_topk(gpann_ctx* ctx, const gpann_points* pts, const float* queries, si
 /* Only the kth distance (Top().first of the reference's heap): out_kth[nq]. */
 int gpann_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
                        float* out_kth);
+/* ComputeGroundTruth (src/recall.h:25-39) over a HOST-resident uint8/int8 point set that is STREAMED through the device:
+ * chunks of chunk_rows rows (0 = 4 Mi rows) are copied H2D on a second stream while the previous chunk is laid out and
+ * scanned by the tcgen05 kernel; the running top-k and per-query bounds carry from chunk to chunk.  Same results as
+ * gpann_points_upload_bytes + gpann_topk, at max(PCIe time, scan time) instead of their sum, and with O(chunk) device
+ * memory.  Pin host_rows (cudaHostAlloc / cudaHostRegister) for the copies to overlap.  d <= 128, k <= 448, L2, queries
+ * integer-valued in the storage range (else GPANN_E_UNSUPPORTED: use gpann_points_upload* + gpann_topk). */
+int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                            const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
+                            uint32_t* out_count);
+/* Device-output form for the multi-GPU path: queries and the [nq,k] key block live on the device, work is enqueued on
+ * `stream` (H2D copies on the ctx's copy stream) and the call returns without synchronising. */
+int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                                   const float* dev_queries, size_t nq, int k, size_t chunk_rows, uint64_t* dev_out_keys,
+                                   void* stream);
+
 /* Device-resident form: dev_queries = nq x d floats in device memory; dev_out_keys = [nq,k] uint64 keys
  * ascending (GPANN_EMPTY_KEY padded).  Asynchronous on `stream`.  This is the per-shard step of the
  * multi-GPU path: every rank runs it on its shard, all-gathers the keys and calls gpann_merge_keys_device. */

@@ -265,3 +265,21 @@ def test_tensor_float_matches_stream_kernel_large(ctx, gpann_mod):
     ctx.set_algo(gpann_mod.ALGO_AUTO)
     assert np.array_equal(i1[:64], i0) and np.array_equal(d1[:64].view(np.uint32), d0.view(np.uint32))
     assert (np.diff(d1, axis=1) >= 0).all() and all(len(set(r)) == k for r in i1)
+
+
+# ---- streamed scan of a host-resident byte set (gpann_topk_stream_bytes): chunking must not change anything ----------
+@pytest.mark.parametrize("n,d,nq,k,chunk,dtype", [
+    (100_000, 128, 300, 10, 30_000, np.uint8), (70_001, 100, 129, 10, 8192, np.int8), (5000, 128, 40, 100, 0, np.uint8),
+    (300, 64, 33, 10, 256, np.uint8), (40_000, 32, 200, 1, 10_000, np.uint8),
+])
+def test_stream_bytes_matches_oracle(ctx, oracle, n, d, nq, k, chunk, dtype):
+    rng = np.random.default_rng(n + k)
+    lo, hi = (0, 256) if dtype == np.uint8 else (-128, 128)
+    P = rng.integers(lo, hi, (n, d)).astype(dtype)
+    if n > 1000:
+        P[n // 2:n // 2 + 50] = P[:50]  # exact duplicates across chunk boundaries: ties must keep the smaller id
+    Q = rng.integers(lo, hi, (nq, d)).astype(np.float32)
+    d1, i1, c1 = ctx.topk_stream_bytes(P, Q, k, id_base=7, chunk_rows=chunk)
+    assert ctx.last_algo.endswith("_stream")
+    d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, k)
+    assert_topk_exact(d1, i1 - 7, d0, i0, c1, c0)
