@@ -49,7 +49,7 @@ struct gpann_ctx {
     // streaming entry points: second stream for the H2D copies, double-buffered raw chunks, one chunk layout
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
-    DevBuf st_raw[2], st_rows, st_norms, st_ids, st_a, st_b, st_c, st_d, st_tmp;
+    DevBuf st_raw[2], st_rows, st_norms, st_ids, st_a, st_b, st_c, st_d, st_tmp, st_narrow;
 };
 
 struct gpann_points {
@@ -509,17 +509,21 @@ int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t
     return 0;
 }
 
-// ---- streamed scan of a HOST-resident byte point set -----------------------------------------------------------
+// ---- streamed scan of a HOST-resident point set -----------------------------------------------------------------
 // The set never sits in HBM as a whole: chunks of `chunk_rows` rows go H2D on a second stream into one of two raw
 // buffers while the previous chunk is turned into a norm-sorted layout and scanned; the running top-k and the per-query
 // bounds carry from chunk to chunk (tc_scan's carry part), so every chunk after the first starts with a tight filter.
-int topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base, const float* dq,
-                      size_t nq, int k, size_t chunk_rows, const TopkOut& out, cudaStream_t st) {
+// Host rows are bytes (u8/s8) or floats; float rows that hold byte values (the reference's reader widens .u8bin/.i8bin
+// to float, src/points_io.cpp:63-111) are narrowed on the device chunk by chunk and take the exact integer kernel,
+// other float rows take the bf16 filter + exact fp32 re-rank against the raw chunk.
+enum HostKind { kHostU8 = 0, kHostS8 = 1, kHostF32 = 2 };
+
+int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int storage, size_t n, size_t d, uint32_t id_base,
+                     const float* dq, size_t nq, int k, size_t chunk_rows, const TopkOut& out, cudaStream_t st) {
     if (d == 0 || d > (size_t) tc::kRowBytes) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: d must be in [1,128]");
     if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream: k must be in [1,448]");
     if ((uint64_t) id_base + n > 0xFFFFFFFFull) return fail(ctx, GPANN_E_ARG, "topk_stream: ids exceed 32 bits (recall.h:30)");
     if (nq == 0) return 0;
-    if (nq > tc_batch_max(ctx, 1)) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: too many queries for one batch");
     if (!ctx->encode_tiled) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: cuTensorMapEncodeTiled unavailable");
     if (!ctx->copy_stream) {
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -528,68 +532,157 @@ int topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d,
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
         }
     }
+    const bool host_f32 = host_kind == kHostF32;
+    const size_t esz = host_f32 ? 4 : 1;
     const size_t tile = tc::kTileN;
-    size_t C = chunk_rows ? chunk_rows : ((size_t) 4 << 20);
+    size_t C = chunk_rows ? chunk_rows : (((size_t) 512 << 20) / (d * esz));  // ~512 MB of host rows per chunk
     C = std::min(((C + tile - 1) / tile) * tile, ((std::max<size_t>(n, 1) + tile - 1) / tile) * tile);
     const size_t nchunks = std::max<size_t>(1, (n + C - 1) / C);
-    for (int b = 0; b < 2; ++b) GP_TRY(reserve(ctx, ctx->st_raw[b], C * d));
-    GP_TRY(reserve(ctx, ctx->st_rows, C * tc::kRowBytes));
-    GP_TRY(reserve(ctx, ctx->st_norms, C * 4));
-    GP_TRY(reserve(ctx, ctx->st_ids, C * 4));
-    GP_TRY(reserve(ctx, ctx->st_a, C * 4));
-    GP_TRY(reserve(ctx, ctx->st_b, C * 4));
-    GP_TRY(reserve(ctx, ctx->st_c, C * 4));
-    GP_TRY(reserve(ctx, ctx->st_d, C * 4));
-    size_t tmp_bytes = 0;
-    sort_pairs_u32(nullptr, tmp_bytes, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_b.p, (uint32_t*) ctx->st_c.p,
-                   (uint32_t*) ctx->st_d.p, C, 25, st);
-    GP_TRY(reserve(ctx, ctx->st_tmp, tmp_bytes));
-    TcPlan pl;
-    int ok = 1;
-    GP_TRY(tc_prepare_queries(ctx, pl, is_signed ? GPANN_STORAGE_S8 : GPANN_STORAGE_U8, (int) d, 0, dq, nq, k, st, &ok));
-    if (!ok) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: queries are not integer-valued in the storage range");
-    CUtensorMap tmap;
-    GP_TRY(encode_rows_map(ctx, &tmap, ctx->st_rows.p, C, tc::kTileN, "chunk"));
-    TcLayout lay;
-    lay.tmap = &tmap;
-    lay.norms = ctx->st_norms.p;
-    lay.ids = (const uint32_t*) ctx->st_ids.p;
-    lay.rows_f32 = nullptr;
     const char* src = (const char*) host_rows;
-    bool timed_any = false;
-    for (size_t c = 0; c < nchunks; ++c) {
-        const int b = (int) (c & 1);
-        const size_t r0 = c * C, rows_c = std::min(C, n - std::min(n, r0));
-        const size_t n_pad = std::max(tile, ((rows_c + tile - 1) / tile) * tile);
-        unsigned char* raw = (unsigned char*) ctx->st_raw[b].p;
-        // raw[b] is free once the gather of the chunk that used it last (this or an earlier call) is done
-        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
-        if (rows_c) CU_TRY(ctx, cudaMemcpyAsync(raw, src + r0 * d, rows_c * d, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-        CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
-        if (rows_c) {
-            launch_byte_norms(raw, rows_c, (int) d, d, is_signed, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_c.p,
-                              blocks_for(ctx, rows_c), st);
-            GP_TRY(check_launch(ctx, "byte_norms_kernel"));
-            size_t tb = ctx->st_tmp.cap;
-            if (sort_pairs_u32(ctx->st_tmp.p, tb, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_b.p, (uint32_t*) ctx->st_c.p,
-                               (uint32_t*) ctx->st_d.p, rows_c, 25, st) != cudaSuccess)
-                return fail(ctx, GPANN_E_CUDA, "topk_stream: radix sort failed");
-            ctx->launches += 4;
+
+    // storage of the scan: bytes for byte hosts; for float hosts AUTO looks at the first chunk (a later chunk that
+    // breaks the guess restarts the call on the float path)
+    if (!host_f32) storage = host_kind == kHostS8 ? GPANN_STORAGE_S8 : GPANN_STORAGE_U8;
+    bool chunk0_resident = false;  // AUTO detection leaves chunk 0 in raw[0]: the first round does not copy it again
+    for (int b = 0; b < 2; ++b) GP_TRY(reserve(ctx, ctx->st_raw[b], C * d * esz));
+    GP_TRY(reserve(ctx, ctx->flags, 64));
+    if (host_f32 && storage == GPANN_STORAGE_AUTO) {
+        const size_t rows0 = std::min(C, n);
+        int flags_h[2] = { 1, 1 };
+        if (rows0) {
+            CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_consumed[0], 0));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->st_raw[0].p, src, rows0 * d * 4, cudaMemcpyHostToDevice, st));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, flags_h, 8, cudaMemcpyHostToDevice, st));
+            launch_detect_bytes((const float*) ctx->st_raw[0].p, rows0 * d, (int*) ctx->flags.p, blocks_for(ctx, rows0 * d), st);
+            GP_TRY(check_launch(ctx, "detect_bytes_kernel"));
+            CU_TRY(ctx, cudaMemcpyAsync(flags_h, ctx->flags.p, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[0], st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            chunk0_resident = true;
         }
-        launch_gather_sorted_rows(raw, rows_c, (int) d, d, (const uint32_t*) ctx->st_d.p, (const uint32_t*) ctx->st_b.p,
-                                  id_base + (uint32_t) r0, n_pad, (unsigned char*) ctx->st_rows.p, (int32_t*) ctx->st_norms.p,
-                                  (uint32_t*) ctx->st_ids.p, blocks_for(ctx, n_pad * 32, 256, 32), st);
-        GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], st));
-        lay.n_pad = n_pad;
-        lay.id_base = id_base + (uint32_t) r0;
-        GP_TRY(tc_scan(ctx, pl, lay, c == 0, true, c == 0, out, 0, st));
-        timed_any = true;
+        storage = flags_h[0] ? GPANN_STORAGE_U8 : (flags_h[1] ? GPANN_STORAGE_S8 : GPANN_STORAGE_F32);
     }
-    (void) timed_any;
-    ctx->last_algo = is_signed ? "tensor_s8_stream" : "tensor_u8_stream";
-    return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, pl.nq_pad, nq, k, out, 0, st);
+    for (;;) {  // at most two rounds: a byte guess refuted by a later chunk falls back to the float path
+        const bool is_float = storage == GPANN_STORAGE_F32;
+        const int is_signed = storage == GPANN_STORAGE_S8;
+        const int dp = is_float ? (int) ((d + 63) / 64) * 64 : 0;
+        if (nq > tc_batch_max(ctx, is_float ? dp / 64 : 1))
+            return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: too many queries for one batch");
+        GP_TRY(reserve(ctx, ctx->st_rows, C * (is_float ? (size_t) dp * 2 : (size_t) tc::kRowBytes)));
+        GP_TRY(reserve(ctx, ctx->st_norms, C * 4));
+        GP_TRY(reserve(ctx, ctx->st_ids, C * 4));
+        GP_TRY(reserve(ctx, ctx->st_a, C * 4));
+        GP_TRY(reserve(ctx, ctx->st_b, C * 4));
+        GP_TRY(reserve(ctx, ctx->st_c, C * 4));
+        GP_TRY(reserve(ctx, ctx->st_d, C * 4));
+        if (host_f32 && !is_float) GP_TRY(reserve(ctx, ctx->st_narrow, C * d));
+        const int sort_bits = is_float ? 32 : 25;
+        size_t tmp_bytes = 0;
+        sort_pairs_u32(nullptr, tmp_bytes, (uint32_t*) ctx->st_a.p, (uint32_t*) ctx->st_b.p, (uint32_t*) ctx->st_c.p,
+                       (uint32_t*) ctx->st_d.p, C, sort_bits, st);
+        GP_TRY(reserve(ctx, ctx->st_tmp, tmp_bytes));
+        TcPlan pl;
+        int ok = 1;
+        GP_TRY(tc_prepare_queries(ctx, pl, storage, (int) d, dp, dq, nq, k, st, &ok));
+        if (!ok) {
+            if (!host_f32) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: queries are not integer-valued in the storage range");
+            storage = GPANN_STORAGE_F32;  // byte-valued points, fractional queries: exact float path
+            continue;
+        }
+        CUtensorMap tmap;
+        GP_TRY(encode_rows_map(ctx, &tmap, ctx->st_rows.p, C, tc::kTileN, "chunk", is_float, is_float ? dp : tc::kRowBytes));
+        TcLayout lay;
+        lay.tmap = &tmap;
+        lay.norms = ctx->st_norms.p;
+        lay.ids = (const uint32_t*) ctx->st_ids.p;
+        lay.rows_f32 = nullptr;
+        if (host_f32 && !is_float) {
+            int flags_h[2] = { 1, 1 };
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, flags_h, 8, cudaMemcpyHostToDevice, st));
+        }
+        for (size_t c = 0; c < nchunks; ++c) {
+            const int b = (int) (c & 1);
+            const size_t r0 = c * C, rows_c = std::min(C, n - std::min(n, r0));
+            const size_t n_pad = std::max(tile, ((rows_c + tile - 1) / tile) * tile);
+            const uint32_t chunk_base = id_base + (uint32_t) r0;
+            unsigned char* raw = (unsigned char*) ctx->st_raw[b].p;
+            // raw[b] is free once the last consumer of the chunk that used it before (this or an earlier call) is done
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+            if (rows_c && !(c == 0 && chunk0_resident))
+                CU_TRY(ctx, cudaMemcpyAsync(raw, src + r0 * d * esz, rows_c * d * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (c == 0) chunk0_resident = false;
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
+            uint32_t *ka = (uint32_t*) ctx->st_a.p, *kb = (uint32_t*) ctx->st_b.p, *va = (uint32_t*) ctx->st_c.p, *vb = (uint32_t*) ctx->st_d.p;
+            const unsigned char* bytes = raw;
+            if (rows_c && host_f32 && !is_float) {  // float host rows holding byte values: check and narrow this chunk
+                launch_detect_bytes((const float*) raw, rows_c * d, (int*) ctx->flags.p, blocks_for(ctx, rows_c * d), st);
+                launch_narrow_rows((const float*) raw, rows_c, (int) d, (int) d, (unsigned char*) ctx->st_narrow.p, blocks_for(ctx, rows_c * d), st);
+                GP_TRY(check_launch(ctx, "detect_bytes_kernel+narrow_rows_kernel", 2));
+                bytes = (const unsigned char*) ctx->st_narrow.p;
+            }
+            if (rows_c) {
+                if (is_float) launch_float_norms((const float*) raw, rows_c, (int) d, ka, va, blocks_for(ctx, rows_c), st);
+                else launch_byte_norms(bytes, rows_c, (int) d, d, is_signed, ka, va, blocks_for(ctx, rows_c), st);
+                GP_TRY(check_launch(ctx, "norms_kernel"));
+                size_t tb = ctx->st_tmp.cap;
+                if (sort_pairs_u32(ctx->st_tmp.p, tb, ka, kb, va, vb, rows_c, sort_bits, st) != cudaSuccess)
+                    return fail(ctx, GPANN_E_CUDA, "topk_stream: radix sort failed");
+                ctx->launches += 4;
+            }
+            if (is_float)
+                launch_gather_sorted_rows_bf16((const float*) raw, rows_c, (int) d, dp, vb, kb, chunk_base, n_pad, (unsigned short*) ctx->st_rows.p,
+                                               (float*) ctx->st_norms.p, (uint32_t*) ctx->st_ids.p, blocks_for(ctx, n_pad * 32, 256, 32), st);
+            else
+                launch_gather_sorted_rows(bytes, rows_c, (int) d, d, vb, kb, chunk_base, n_pad, (unsigned char*) ctx->st_rows.p,
+                                          (int32_t*) ctx->st_norms.p, (uint32_t*) ctx->st_ids.p, blocks_for(ctx, n_pad * 32, 256, 32), st);
+            GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
+            if (!is_float) CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], st));
+            lay.n_pad = n_pad;
+            lay.id_base = chunk_base;
+            lay.rows_f32 = is_float ? (const float*) raw : nullptr;
+            GP_TRY(tc_scan(ctx, pl, lay, c == 0, true, c == 0, out, 0, st));
+            if (is_float) CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], st));  // the re-rank reads the raw rows
+        }
+        if (host_f32 && !is_float) {
+            int flags_h[2] = { 1, 1 };
+            CU_TRY(ctx, cudaMemcpyAsync(flags_h, ctx->flags.p, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            if (!flags_h[is_signed ? 1 : 0]) {  // some later chunk is not byte-valued after all
+                storage = GPANN_STORAGE_F32;
+                continue;
+            }
+        }
+        ctx->last_algo = is_float ? "tensor_bf16_stream" : (is_signed ? "tensor_s8_stream" : "tensor_u8_stream");
+        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, pl.nq_pad, nq, k, out, 0, st);
+    }
+}
+
+int topk_stream_host_api(gpann_ctx* ctx, const void* host_rows, int host_kind, int storage, size_t n, size_t d, uint32_t id_base,
+                         const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
+                         uint32_t* out_count, float* out_kth) {
+    if ((!host_rows && n) || !queries) return fail(ctx, GPANN_E_ARG, "topk_stream: null argument");
+    if (nq == 0) return 0;
+    if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream: k must be in [1,448]");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
+    GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->id_out, nq * k * 4));
+    GP_TRY(reserve(ctx, ctx->cnt_out, nq * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdev.p, queries, nq * d * 4, cudaMemcpyHostToDevice, st));
+    TopkOut o;
+    o.dist = out_dist ? (float*) ctx->dist_out.p : nullptr;
+    o.id = out_id ? (uint32_t*) ctx->id_out.p : nullptr;
+    o.count = out_count ? (uint32_t*) ctx->cnt_out.p : nullptr;
+    o.kth = out_kth ? (float*) ctx->cnt_out.p + nq : nullptr;
+    GP_TRY(topk_stream_host(ctx, host_rows, host_kind, storage, n, d, id_base, (const float*) ctx->qdev.p, nq, k, chunk_rows, o, st));
+    if (out_dist) CU_TRY(ctx, cudaMemcpyAsync(out_dist, o.dist, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_id) CU_TRY(ctx, cudaMemcpyAsync(out_id, o.id, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_count) CU_TRY(ctx, cudaMemcpyAsync(out_count, o.count, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (out_kth) CU_TRY(ctx, cudaMemcpyAsync(out_kth, o.kth, nq * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
 }
 
 int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
@@ -922,7 +1015,7 @@ void gpann_destroy(gpann_ctx* ctx) {
                        &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info };
     for (DevBuf* b : bufs) release(*b);
     DevBuf* sbufs[] = { &ctx->st_raw[0], &ctx->st_raw[1], &ctx->st_rows, &ctx->st_norms, &ctx->st_ids, &ctx->st_a, &ctx->st_b,
-                        &ctx->st_c, &ctx->st_d, &ctx->st_tmp };
+                        &ctx->st_c, &ctx->st_d, &ctx->st_tmp, &ctx->st_narrow };
     for (DevBuf* b : sbufs) release(*b);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2; ++i) {
@@ -1134,26 +1227,16 @@ int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, siz
                             const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
                             uint32_t* out_count) {
     if (!ctx) return GPANN_E_ARG;
-    if ((!host_rows && n) || !queries) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes: null argument");
-    if (nq == 0) return 0;
-    if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes: k must be in [1,448]");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
-    GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
-    GP_TRY(reserve(ctx, ctx->id_out, nq * k * 4));
-    GP_TRY(reserve(ctx, ctx->cnt_out, nq * 8));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdev.p, queries, nq * d * 4, cudaMemcpyHostToDevice, st));
-    TopkOut o;
-    o.dist = out_dist ? (float*) ctx->dist_out.p : nullptr;
-    o.id = out_id ? (uint32_t*) ctx->id_out.p : nullptr;
-    o.count = out_count ? (uint32_t*) ctx->cnt_out.p : nullptr;
-    GP_TRY(topk_stream_bytes(ctx, host_rows, n, d, is_signed, id_base, (const float*) ctx->qdev.p, nq, k, chunk_rows, o, st));
-    if (out_dist) CU_TRY(ctx, cudaMemcpyAsync(out_dist, o.dist, nq * k * 4, cudaMemcpyDeviceToHost, st));
-    if (out_id) CU_TRY(ctx, cudaMemcpyAsync(out_id, o.id, nq * k * 4, cudaMemcpyDeviceToHost, st));
-    if (out_count) CU_TRY(ctx, cudaMemcpyAsync(out_count, o.count, nq * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
-    return 0;
+    return topk_stream_host_api(ctx, host_rows, is_signed ? kHostS8 : kHostU8, 0, n, d, id_base, queries, nq, k, chunk_rows, out_dist,
+                                out_id, out_count, nullptr);
+}
+
+int gpann_topk_stream(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base, const float* queries,
+                      size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id, uint32_t* out_count, float* out_kth) {
+    if (!ctx) return GPANN_E_ARG;
+    if (storage < GPANN_STORAGE_AUTO || storage > GPANN_STORAGE_S8) return fail(ctx, GPANN_E_ARG, "topk_stream: bad storage");
+    return topk_stream_host_api(ctx, host_rows, kHostF32, storage, n, d, id_base, queries, nq, k, chunk_rows, out_dist, out_id,
+                                out_count, out_kth);
 }
 
 int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
@@ -1164,7 +1247,8 @@ int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     TopkOut o;
     o.keys = dev_out_keys;
-    return topk_stream_bytes(ctx, host_rows, n, d, is_signed, id_base, dev_queries, nq, k, chunk_rows, o, (cudaStream_t) stream);
+    return topk_stream_host(ctx, host_rows, is_signed ? kHostS8 : kHostU8, 0, n, d, id_base, dev_queries, nq, k, chunk_rows, o,
+                            (cudaStream_t) stream);
 }
 
 int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,

@@ -1,7 +1,7 @@
 // recall.h -- drop-in for gp-ann's src/recall.h.  Like the reference's header it DEFINES its functions (include it
 // from one translation unit per executable).
 //   ComputeDistanceToKthNeighbor (:10-23) and ComputeGroundTruth (:25-39): the n*nq scan runs on the GPU through
-//   gpann_kth_distance / gpann_topk; results are the k lexicographically smallest (distance,id) per query,
+//   gpann_topk_stream (host rows streamed in chunks) or gpann_points_upload + gpann_topk / gpann_kth_distance; results are the k lexicographically smallest (distance,id) per query,
 //   ascending, min(k,n) entries (topn.h:21-29).
 //   OracleRecall (:41-68), ConvertGroundTruthToDistanceToKthNeighbor (:74-137), Recall (:139-150): O(nq*k) host
 //   bookkeeping, kept on the CPU with the reference's behaviour and printed text.
@@ -19,12 +19,32 @@
 #include "gpann_dropin.h"
 #include "topn.h"
 
+namespace gpann_dropin {
+// L2, d <= 128: the host PointSet is streamed through the device chunk by chunk (gpann_topk_stream: H2D overlapped with
+// the scan, byte-valued rows narrowed on the device); everything else uploads the set and scans it resident.  Both are
+// GPU paths -- GPANN_E_UNSUPPORTED from the first only selects the second.
+inline void topk_any(Session& s, PointSet& points, PointSet& queries, int k, float* dist, uint32_t* ids, uint32_t* count,
+                     float* kth) {
+    if (kMetric == GPANN_METRIC_L2 && points.d <= 128 && k <= 448) {
+        const int rc = gpann_topk_stream(s.ctx, points.coordinates.data(), points.n, points.d, GPANN_STORAGE_AUTO, 0,
+                                         queries.coordinates.data(), queries.n, k, 0, dist, ids, count, kth);
+        if (rc != GPANN_E_UNSUPPORTED) {
+            s.check(rc);
+            return;
+        }
+    }
+    DevicePoints<PointSet> dp(s, points);
+    if (dist || ids || count)
+        s.check(gpann_topk(s.ctx, dp.h, queries.coordinates.data(), queries.n, k, kMetric, dist, ids, count));
+    if (kth) s.check(gpann_kth_distance(s.ctx, dp.h, queries.coordinates.data(), queries.n, k, kMetric, kth));
+}
+}  // namespace gpann_dropin
+
 std::vector<float> ComputeDistanceToKthNeighbor(PointSet& points, PointSet& queries, int k) {
     auto& s = gpann_dropin::session();
     std::lock_guard<std::mutex> lock(s.mutex);
     std::vector<float> kth(queries.n);
-    gpann_dropin::DevicePoints<PointSet> dp(s, points);
-    s.check(gpann_kth_distance(s.ctx, dp.h, queries.coordinates.data(), queries.n, k, gpann_dropin::kMetric, kth.data()));
+    gpann_dropin::topk_any(s, points, queries, k, nullptr, nullptr, nullptr, kth.data());
     return kth;
 }
 
@@ -34,11 +54,7 @@ std::vector<NNVec> ComputeGroundTruth(PointSet& points, PointSet& queries, int k
     const size_t nq = queries.n;
     std::vector<float> dist(nq * k);
     std::vector<uint32_t> ids(nq * k), count(nq);
-    {
-        gpann_dropin::DevicePoints<PointSet> dp(s, points);
-        s.check(gpann_topk(s.ctx, dp.h, queries.coordinates.data(), nq, k, gpann_dropin::kMetric, dist.data(), ids.data(),
-                           count.data()));
-    }
+    gpann_dropin::topk_any(s, points, queries, k, dist.data(), ids.data(), count.data(), nullptr);
     std::vector<NNVec> res(nq);
     for (size_t q = 0; q < nq; ++q) {
         res[q].resize(count[q]);

@@ -36,6 +36,7 @@ SYMBOLS = {
     "gpann_kth_distance": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "gpann_topk_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
     "gpann_topk_stream_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp]),
+    "gpann_topk_stream": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp, _vp]),
     "gpann_topk_stream_bytes_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp]),
     "gpann_topk_range": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "gpann_merge_keys_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
@@ -202,6 +203,17 @@ class Context:
         self.check(self.lib.gpann_topk_stream_bytes(self.h, _ptr(rows), rows.shape[0], rows.shape[1], int(rows.dtype == np.int8),
                                                     id_base, _ptr(q), nq, k, chunk_rows, _ptr(dist), _ptr(ids), _ptr(cnt)))
         return dist, ids, cnt
+
+    def topk_stream(self, host_rows, queries, k, storage=STORAGE_AUTO, id_base=0, chunk_rows=0, want_kth=False):
+        """Exact top-k against host-resident float rows streamed through the device in chunks."""
+        rows = np.ascontiguousarray(host_rows, dtype=np.float32)
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        dist, ids, cnt = np.empty((nq, k), np.float32), np.empty((nq, k), np.uint32), np.empty(nq, np.uint32)
+        kth = np.empty(nq, np.float32) if want_kth else None
+        self.check(self.lib.gpann_topk_stream(self.h, _ptr(rows), rows.shape[0], rows.shape[1], storage, id_base, _ptr(q), nq, k,
+                                              chunk_rows, _ptr(dist), _ptr(ids), _ptr(cnt), _ptr(kth)))
+        return (dist, ids, cnt, kth) if want_kth else (dist, ids, cnt)
 
     def topk_stream_bytes_device(self, host_ptr, n, d, is_signed, dev_queries, nq, k, dev_out_keys, id_base=0, chunk_rows=0,
                                  stream=None):

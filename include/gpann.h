@@ -102,6 +102,12 @@ int gpann_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* que
 int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
                             const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
                             uint32_t* out_count);
+/* The same for FLOAT host rows (PointSet::coordinates, src/defs.h:10-21): with storage AUTO, rows holding byte values
+ * (the reference's reader widens .u8bin/.i8bin to float, src/points_io.cpp:63-111) are narrowed on the device chunk by
+ * chunk and scanned by the exact integer kernel; other rows take the bf16 filter + exact fp32 re-rank against the raw
+ * chunk.  out_kth (optional) receives the k-th distance per query (ComputeDistanceToKthNeighbor, src/recall.h:10-23). */
+int gpann_topk_stream(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base, const float* queries,
+                      size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id, uint32_t* out_count, float* out_kth);
 /* Device-output form for the multi-GPU path: queries and the [nq,k] key block live on the device, work is enqueued on
  * `stream` (H2D copies on the ctx's copy stream) and the call returns without synchronising. */
 int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,

@@ -283,3 +283,31 @@ def test_stream_bytes_matches_oracle(ctx, oracle, n, d, nq, k, chunk, dtype):
     assert ctx.last_algo.endswith("_stream")
     d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, k)
     assert_topk_exact(d1, i1 - 7, d0, i0, c1, c0)
+
+
+@pytest.mark.parametrize("n,d,nq,k,chunk", [(60_000, 96, 200, 10, 16_384), (20_000, 100, 64, 100, 0), (9000, 128, 300, 10, 2048)])
+def test_stream_float_rows_matches_oracle(ctx, oracle, n, d, nq, k, chunk):
+    rng = np.random.default_rng(n)
+    P = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    d1, i1, c1, kth = ctx.topk_stream(P, Q, k, chunk_rows=chunk, want_kth=True)
+    assert ctx.last_algo == "tensor_bf16_stream"
+    d0, i0, c0 = oracle.ground_truth(P, Q, k)
+    assert_topk_close(d1, i1, d0, i0)
+    np.testing.assert_allclose(kth, d0[:, k - 1], rtol=REL)
+
+
+def test_stream_float_rows_holding_bytes_take_the_integer_kernel(ctx, oracle):
+    rng = np.random.default_rng(77)
+    P = rng.integers(0, 256, (50_000, 128)).astype(np.float32)
+    Q = rng.integers(0, 256, (150, 128)).astype(np.float32)
+    d1, i1, c1 = ctx.topk_stream(P, Q, 10, chunk_rows=12_000)
+    assert ctx.last_algo == "tensor_u8_stream"
+    d0, i0, c0 = oracle.ground_truth(P, Q, 10)
+    assert_topk_exact(d1, i1, d0, i0, c1, c0)
+    # a later chunk that is not byte-valued refutes the first chunk's guess: the call restarts on the float path
+    P[40_000, 3] = 0.5
+    d1, i1, c1 = ctx.topk_stream(P, Q, 10, chunk_rows=12_000)
+    assert ctx.last_algo == "tensor_bf16_stream"
+    d0, i0, c0 = oracle.ground_truth(P, Q, 10)
+    assert_topk_close(d1, i1, d0, i0)
