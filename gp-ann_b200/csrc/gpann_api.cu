@@ -39,6 +39,8 @@ struct gpann_ctx {
     EncodeTiledFn encode_tiled = nullptr;
     int tc_mode = 0;     // GPANN_TC_MODE env: 1 = probe (MMA + TMEM loads + max), 2 = probe (MMA issue only)
     int tc_prepass = 1;  // GPANN_TC_PREPASS env: 0 disables the sample pre-pass (cold-start thresholds)
+    int tc_warm = 0;     // GPANN_TC_WARM env (probe): keep the previous call's k-th distances as the next call's bounds
+    bool tc_warm_valid = false;
     int timing = 0;
     bool timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -383,13 +385,14 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
     if (pl.is_float) {
         GP_TRY(reserve(ctx, ctx->qf32, pl.nq_pad * d * sizeof(float)));
         launch_prep_queries_bf16(dq, (int) nqb, d, dp, (int) pl.nq_pad, (unsigned short*) ctx->qrows.p, (float*) ctx->qnorm.p,
-                                 (float*) ctx->qf32.p, (uint32_t*) ctx->bound.p, st);
+                                 (float*) ctx->qf32.p, (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
         GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
     } else {
         int one = 1;
         CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
         launch_prep_queries_bytes(dq, (int) nqb, d, (int) pl.nq_pad, pl.is_signed, (unsigned char*) ctx->qrows.p,
-                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p, (uint32_t*) ctx->bound.p, st);
+                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p,
+                                  (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
         GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
         int okh = 0;
         CU_TRY(ctx, cudaMemcpyAsync(&okh, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
@@ -446,10 +449,11 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     const size_t smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap);
     // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
     // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
-    // (a cold start pushes EVERY distance through the selection warps).  Two levels: 1 tile per split (cold, but
-    // tiny), then 12 tiles per split filtered by the level-1 bound.
-    if (prepass && ctx->tc_prepass && ctx->tc_mode == 0) {
-        const uint32_t levels[2] = { 1, 12 };
+    // (a cold start pushes EVERY distance through the selection warps).  Three levels: 1 tile per split (cold, but
+    // tiny), then 12 and 160 tiles per split, each filtered by the previous level's bound.  (During a pass the CTAs of
+    // different point splits also share their k-th distances through a.bound, see publish_threshold.)
+    if (prepass && ctx->tc_prepass && ctx->tc_mode == 0 && !(ctx->tc_warm && ctx->tc_warm_valid)) {
+        const uint32_t levels[3] = { 1, 12, 160 };
         for (uint32_t per_split : levels) {
             const uint32_t nsample = (uint32_t) S * per_split;
             if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
@@ -467,6 +471,12 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.tile_lo = 0;
     a.tile_stride = 1;
     a.ntiles = tiles_total;
+    static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
+    if (want_stats) {
+        GP_TRY(reserve(ctx, ctx->misc, 64));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 16, st));
+        a.stats = (unsigned long long*) ctx->misc.p;
+    }
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
     launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
     if (ctx->timing) {
@@ -474,7 +484,22 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
         ctx->timed = true;
     }
     GP_TRY(check_launch(ctx, "topk_tc_kernel"));
-    if (!carry) return launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, out, q_off, st);
+    if (want_stats) {
+        unsigned long long h[2] = { 0, 0 };
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, ctx->misc.p, 16, cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u\n", h[0], h[1], grid);
+    }
+    if (!carry) {
+        if (ctx->tc_warm) {  // probe: the final k-th distances become the next call's bounds
+            TopkOut b;
+            b.kth = (float*) ctx->bound.p;
+            b.kth_full_only = 1;
+            GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st));
+            ctx->tc_warm_valid = true;
+        }
+        return launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, out, q_off, st);
+    }
     TopkOut c;
     c.keys = carry_keys;              // in place: a warp reads all parts of its query before it writes
     c.kth = (float*) ctx->bound.p;
@@ -999,6 +1024,8 @@ int gpann_init(gpann_ctx** out, int device) {
     ctx->tc_mode = mode ? std::atoi(mode) : 0;
     const char* kmm = std::getenv("GPANN_KM_MODE");
     ctx->km_mode = kmm ? std::atoi(kmm) : 0;
+    const char* warm = std::getenv("GPANN_TC_WARM");
+    ctx->tc_warm = warm ? std::atoi(warm) : 0;
     const char* pre = std::getenv("GPANN_TC_PREPASS");
     ctx->tc_prepass = pre ? std::atoi(pre) : 1;
     *out = ctx;

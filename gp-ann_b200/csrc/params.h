@@ -109,19 +109,20 @@ struct Args {
     uint64_t* cand;          // [grid, R*128, cap] per-query key lists (global, touched by the selection warps only)
     uint64_t* partial;       // [S, G*R*128, k]
     uint32_t* bound;         // [G*R*128] upper bound on each query's kth distance from the sample passes (float bits)
-    int mode;                // 0 = full; probes with invalid results: 1 = MMA + TMEM loads + max, 2 = MMA issue only
+    int mode;                // 0 = full; probes with invalid results: 1 = MMA + TMEM loads + max, 2 = MMA issue only, 3 = TMEM loads + max only
     // float path only: the exact re-rank reads the original fp32 rows
     const float* rows_f32;   // [n, d] original point rows
     const float* q_f32;      // [G*R*128, d] queries (zero padded)
     int d;
     uint32_t id_base;
     float eps;               // relative error bound of the bf16 dot product: |dot~ - dot| <= eps*|q|*|x|
+    unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
 };
 
 // Shared-memory footprint (+1 KB so the operand area can be aligned to 1024 bytes).
 inline size_t smem_bytes(int R, int kblocks, int stages, int qcap) {
     return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
-           (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 12 /*queues*/ +
+           (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 16 /*queues*/ +
            (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {

@@ -98,7 +98,7 @@ __global__ void prep_queries_bytes_kernel(const float* q, int nq, int d, int nq_
         reinterpret_cast<uint32_t*>(out_rows + (size_t) r * 128)[lane] = word;
         if (lane == 0) {
             out_norms[r] = nrm;
-            if (bound) bound[r] = 0x7f800000u;  // +inf: no bound yet
+            if (bound) if (bound) bound[r] = 0x7f800000u;  // +inf: no bound yet
         }
         if (!__all_sync(0xffffffffu, good) && lane == 0) atomicAnd(ok, 0);
     }
@@ -158,7 +158,7 @@ __global__ void prep_queries_bf16_kernel(const float* q, int nq, int d, int dp, 
         for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
         if (lane == 0) {
             out_norms[r] = nrm;
-            bound[r] = 0x7f800000u;
+            if (bound) bound[r] = 0x7f800000u;
         }
     }
 }

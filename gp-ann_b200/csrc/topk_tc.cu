@@ -73,11 +73,20 @@ constexpr uint32_t kQEmpty = 0xFFFFFFFFu;
 
 struct Queue {
     uint32_t cap;             // records (power of two)
-    uint64_t* key;            // [cap]
-    volatile uint32_t* qs;    // [cap]
+    uint4* rec;               // [cap] {key lo, key hi, query slot (kQEmpty = free), -}: written and read as ONE 16-byte
+                              // shared-memory access, so a record needs no fence between its payload and its ready flag
     uint32_t* tail;           // reserved by producers (atomicAdd)
     volatile uint32_t* head;  // consumed (written by the consumer's lane 0)
 };
+
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4_volatile(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
 
 __device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs) {
     const uint32_t pos = atomicAdd(q.tail, 1u);
@@ -88,25 +97,45 @@ __device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t q
             if (global_timer_ns() - t0 > 4000000000ull) __trap();
         }
     }
-    const uint32_t slot = pos & (q.cap - 1);
-    q.key[slot] = key;
-    __threadfence_block();
-    q.qs[slot] = qs;
+    st_shared_v4(q.rec + (pos & (q.cap - 1)), (uint32_t) key, (uint32_t) (key >> 32), qs, 0u);
+}
+
+// v[j] for a run-time j without local memory: a 5-level tree of selects on the bits of j (31 SEL, depth 5).
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+    uint32_t a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+    const uint32_t d0 = (j & 8) ? c[1] : c[0], d1 = (j & 8) ? c[3] : c[2];
+    return (j & 16) ? d1 : d0;
 }
 
 // Exact re-test of the values of one 32-column chunk that reached the filter threshold: compute the integer
-// distance, build the (distance,id) key and hand it to the selection warp that owns the query.
+// distance, build the (distance,id) key and hand it to the selection warp that owns the query.  Branch-free scan:
+// a chain of 32 compare+branch pairs costs a lone hit lane ~15 cycles per untaken branch (in-order issue), and every
+// cycle a filter warp loses here delays the whole TMEM pipeline, so the hits are collected into a bit mask first.
 __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, const int32_t* tn, const uint32_t* ti, int col0,
                                               int nqv, uint32_t qs, const Queue& q) {
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int acc = (int) v[j];
-        if (acc >= T) {
-            const uint32_t id = ti[col0 + j];
-            if (id != kInvalidId) {
-                const int dist = nqv + tn[col0 + j] - 2 * acc;
-                queue_push(q, pack_key((float) dist, id), qs);
-            }
+    for (int j = 0; j < 8; ++j) {
+        m0 |= ((int) v[j] >= T) ? (1u << j) : 0u;
+        m1 |= ((int) v[j + 8] >= T) ? (1u << (j + 8)) : 0u;
+        m2 |= ((int) v[j + 16] >= T) ? (1u << (j + 16)) : 0u;
+        m3 |= ((int) v[j + 24] >= T) ? (1u << (j + 24)) : 0u;
+    }
+    uint32_t mask = (m0 | m1) | (m2 | m3);
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t id = ti[col0 + j];
+        if (id != kInvalidId) {
+            const int acc = (int) pick32(v, j);
+            const int dist = nqv + tn[col0 + j] - 2 * acc;
+            queue_push(q, pack_key((float) dist, id), qs);
         }
     }
 }
@@ -115,12 +144,20 @@ __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, co
 // selection warp recomputes the exact fp32 distance.
 __device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T, const uint32_t* ti, int col0, uint32_t qs,
                                                 const Queue& q) {
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (__uint_as_float(v[j]) >= T) {
-            const uint32_t id = ti[col0 + j];
-            if (id != kInvalidId) queue_push(q, (uint64_t) id, qs);
-        }
+    for (int j = 0; j < 8; ++j) {
+        m0 |= (__uint_as_float(v[j]) >= T) ? (1u << j) : 0u;
+        m1 |= (__uint_as_float(v[j + 8]) >= T) ? (1u << (j + 8)) : 0u;
+        m2 |= (__uint_as_float(v[j + 16]) >= T) ? (1u << (j + 16)) : 0u;
+        m3 |= (__uint_as_float(v[j + 24]) >= T) ? (1u << (j + 24)) : 0u;
+    }
+    uint32_t mask = (m0 | m1) | (m2 | m3);
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t id = ti[col0 + j];
+        if (id != kInvalidId) queue_push(q, (uint64_t) id, qs);
     }
 }
 
@@ -131,6 +168,10 @@ struct SelState {
     int* cnt;        // keys held in the query's list
     int* maxpos;     // position of the k-th best (largest kept) key in the unsorted list (k <= 32)
     const int* nq;   // |q|^2
+    uint32_t* gbound;  // global [nslots]: float bits of the best known upper bound on each query's k-th distance, shared by
+                       // every CTA (point split) that serves the same queries -- atomicMin when a list tightens, re-read
+                       // while the selection warp idles
+    int nslots;
     uint64_t* lists; // global: [nslots][cap] keys of this CTA
     int k, cap;
     // float path: exact re-rank inputs
@@ -185,12 +226,29 @@ __device__ __forceinline__ float exact_sqr_l2(const float* __restrict__ x, const
 // Insert one record.  k <= 32: unsorted list of the k best with replace-the-maximum (exact threshold after every
 // insert).  Larger k: append; the caller compacts a full list warp-wide.  Returns true if the list needs compaction.
 template <bool kFloat>
-__device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs, uint64_t kth) {
+__device__ __forceinline__ void apply_bound(const SelState& s, uint32_t qs, float kth_dist) {
     if (kFloat) {  // U = |q|^2 - kth (float bits in the int arrays); monotone non-decreasing
-        const float u = __int_as_float(s.nq[qs]) - key_dist(kth);
+        const float u = __int_as_float(s.nq[qs]) - kth_dist;
         s.U[qs] = __float_as_int(fmaxf(__int_as_float(s.U[qs]), u));
     } else {
-        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) key_dist(kth));
+        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) kth_dist);
+    }
+}
+template <bool kFloat>
+__device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs, uint64_t kth) {
+    const float kd = key_dist(kth);
+    apply_bound<kFloat>(s, qs, kd);
+    // distances are non-negative, so their bit patterns order like unsigned integers
+    if (s.gbound && kd >= 0.f) atomicMin(s.gbound + qs, __float_as_uint(kd));
+}
+// Pull the bounds other point splits have published for this selection warp's queries into the filter thresholds.
+template <bool kFloat>
+__device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int lane) {
+    if (!s.gbound) return;
+    for (int base = sel * 32; base < s.nslots; base += 32 * kSelWarps) {
+        const uint32_t qs = (uint32_t) (base + lane);
+        const float b = __uint_as_float(__ldcg(s.gbound + qs));
+        if (b < 3.0e38f) apply_bound<kFloat>(s, qs, b);
     }
 }
 
@@ -233,8 +291,8 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
 }
 
 template <bool kFloat>
-__device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane) {
-    uint32_t head = 0;
+__device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel) {
+    uint32_t head = 0, idle = 0;
     while (true) {
         const uint32_t finished = *done;  // read BEFORE the tail: once all producers are done the tail is final
         __threadfence_block();
@@ -242,6 +300,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         const uint32_t avail = tail - head;
         if (avail == 0) {
             if (finished == (uint32_t) kEpiWarps) break;
+            if ((++idle & 31u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~10 us of idling
             __nanosleep(200);
             continue;
         }
@@ -250,18 +309,17 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         uint64_t key = 0;
         bool pending = (uint32_t) lane < n;
         if (pending) {
-            const uint32_t slot = (head + lane) & (q.cap - 1);
-            uint32_t w = q.qs[slot];
-            if (w == kQEmpty) {
+            uint4* slot = q.rec + ((head + lane) & (q.cap - 1));
+            uint4 r = ld_shared_v4_volatile(slot);
+            if (r.z == kQEmpty) {
                 const uint64_t t0 = global_timer_ns();
-                while ((w = q.qs[slot]) == kQEmpty) {
+                while ((r = ld_shared_v4_volatile(slot)).z == kQEmpty) {
                     if (global_timer_ns() - t0 > 4000000000ull) __trap();
                 }
             }
-            __threadfence_block();
-            key = q.key[slot];
-            qs = w;
-            q.qs[slot] = kQEmpty;
+            key = ((uint64_t) r.y << 32) | r.x;
+            qs = r.z;
+            reinterpret_cast<volatile uint32_t*>(slot)[2] = kQEmpty;
         }
         __threadfence_block();
         __syncwarp();
@@ -321,9 +379,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int32_t* s_norm = reinterpret_cast<int32_t*>(after + 256);                 // [NST][256] int32 or float bits
     uint32_t* s_id = reinterpret_cast<uint32_t*>(s_norm + NST * kTileN);       // [NST][256]
     uint64_t* s_kth = reinterpret_cast<uint64_t*>(s_id + NST * kTileN);        // [R*128]
-    uint64_t* s_qkey = s_kth + R * kTileM;                                     // [kSelWarps][qcap]
-    uint32_t* s_qqs = reinterpret_cast<uint32_t*>(s_qkey + kSelWarps * a.qcap);  // [kSelWarps][qcap]
-    int* s_U = reinterpret_cast<int*>(s_qqs + kSelWarps * a.qcap);             // [R*128] int or float bits
+    uint4* s_qrec = reinterpret_cast<uint4*>(s_kth + R * kTileM);              // [kSelWarps][qcap] 16-byte records
+    int* s_U = reinterpret_cast<int*>(s_qrec + kSelWarps * a.qcap);            // [R*128] int or float bits
     int* s_cnt = s_U + R * kTileM;
     int* s_nq = s_cnt + R * kTileM;                                            // int or float bits
     int* s_maxpos = s_nq + R * kTileM;
@@ -346,7 +403,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             s_U[i] = (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
         }
     }
-    for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qqs[i] = kQEmpty;
+    for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qrec[i] = make_uint4(0u, 0u, kQEmpty, 0u);
     if (tid < 8) s_ctr[tid] = 0;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_p);
@@ -414,6 +471,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                         const int kb = ks >> 2, w = ks & 3;
                         const uint64_t adesc = make_sw128_desc(sQ + r * q_tile_bytes + kb * kQBlockBytes) + 2 * w;
                         const uint64_t bdesc = make_sw128_desc(sP + st * p_tile_bytes + kb * kPBlockBytes) + 2 * w;
+                        if (a.mode == 3) continue;  // probe: no MMA at all, the drain rate alone
                         if (kFloat) umma_bf16(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
                         else umma_i8(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
                     }
@@ -431,7 +489,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const int qrow = wq * 32 + lane;
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
         const int col_base = half * (kTileN / 2);
-        uint32_t it = 0;
+        uint32_t it = 0, slow_entries = 0;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
             const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
@@ -468,8 +526,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 const int sel = (int) (qs >> 5) & (kSelWarps - 1);
                 Queue q;
                 q.cap = (uint32_t) a.qcap;
-                q.key = s_qkey + sel * a.qcap;
-                q.qs = s_qqs + sel * a.qcap;
+                q.rec = s_qrec + sel * a.qcap;
                 q.tail = s_ctr + sel;
                 q.head = s_ctr + kSelWarps + sel;
                 mbar_wait(bar_tfull + 8 * slot, sph);
@@ -489,9 +546,14 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                     tmem_ld32(tbase + c * 64, va);
                     tmem_ld32(tbase + c * 64 + 32, vb);
                     tmem_wait_ld();
+                    if (c == kTileN / 128 - 1) {  // accumulator drained into registers: hand the slot back before the
+                        tcgen05_fence_before();   // arithmetic, so a slow-path entry on this half cannot stall the MMA
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+                    }
                     if (kFloat) {
                         const float ma = max32f(va), mb = max32f(vb);
-                        if (a.mode == 1) {
+                        if (a.mode == 1 || a.mode == 3) {
                             if (fmaxf(ma, mb) == 3.0e38f) s_U[qs] = __float_as_int(ma);
                             continue;
                         }
@@ -502,34 +564,32 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                         }
                     } else {
                         const int ma = max32(va), mb = max32(vb);
-                        if (a.mode == 1) {  // probe: keep the loads and the max alive, skip selection
+                        if (a.mode == 1 || a.mode == 3) {  // probe: keep the loads and the max alive, skip selection
                             if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
                             continue;
                         }
                         if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
+                            ++slow_entries;
                             if (ma >= Ti) enqueue_chunk(va, Ti, tn, ti, col_base + c * 64, nqraw, qs, q);
                             if (mb >= Ti) enqueue_chunk(vb, Ti, tn, ti, col_base + c * 64 + 32, nqraw, qs, q);
                             __syncwarp();
                         }
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms/ids
         }
         __threadfence_block();
         __syncwarp();
+        if (a.stats && lane == 0) atomicAdd(a.stats + 1, (unsigned long long) slow_entries);
         if (lane == 0) atomicAdd(s_ctr + 2 * kSelWarps, 1u);  // done: every record of this warp is in a queue
     } else {
         // ===== selection warps: exact per-query top-k lists, thresholds published through s_U =====
         const int sel = warp - (2 + kEpiWarps);
         Queue q;
         q.cap = (uint32_t) a.qcap;
-        q.key = s_qkey + sel * a.qcap;
-        q.qs = s_qqs + sel * a.qcap;
+        q.rec = s_qrec + sel * a.qcap;
         q.tail = s_ctr + sel;
         q.head = s_ctr + kSelWarps + sel;
         SelState ss;
@@ -545,7 +605,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.q_f32 = a.q_f32 ? a.q_f32 + qbase * a.d : nullptr;
         ss.d = a.d;
         ss.id_base = a.id_base;
-        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane);
+        ss.gbound = a.bound ? a.bound + qbase : nullptr;
+        ss.nslots = nslots;
+        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel);
+        if (a.stats && lane == 0) atomicAdd(a.stats, (unsigned long long) *q.tail);  // records pushed to this queue
     }
 
     // ---- final selection: every query's k best of this CTA's point range -> partial[s], by all non-role warps ----
