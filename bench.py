@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "gp-ann_b200")):
         sys.path.insert(0, p)
 
 N_TOTAL = int(os.environ.get("GPANN_BENCH_N", 100_000_000))
-D = 128
+D = int(os.environ.get("GPANN_BENCH_D", 128))  # probes only; the workload is d = 128
 NQ = int(os.environ.get("GPANN_BENCH_NQ", 10_000))
 K = 10
 METRIC = "exact_top10_knn_distance_evals_per_s"

@@ -11,8 +11,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-OUT = os.path.join(HERE, "libgpann_cuda.so")
+# experiment hooks: GPANN_NVCC_EXTRA="-DX=1 ..." adds flags, GPANN_BUILD_TAG=name builds libgpann_cuda_name.so in build_name/
+TAG = os.environ.get("GPANN_BUILD_TAG", "")
+EXTRA = os.environ.get("GPANN_NVCC_EXTRA", "").split()
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+OUT = os.path.join(HERE, "libgpann_cuda" + ("_" + TAG if TAG else "") + ".so")
 SOURCES = ["gpann_api.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
 HEADERS = ["common.cuh", "distance.cuh", "params.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "gpann.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -34,7 +37,7 @@ def _compile(src, force, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if force or _stale(obj, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
@@ -51,7 +54,8 @@ def build(force=False, verbose=False):
     objs = [o for o, _ in results]
     if force or any(changed for _, changed in results) or not os.path.exists(OUT):
         subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
-    build_dropin(force)
+    if not TAG:
+        build_dropin(force)
     return OUT
 
 

@@ -19,8 +19,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait, optionally with a suspend-time hint (GPANN_TRYWAIT_HINT ns; 0 = the hardware's default time limit).
+#ifndef GPANN_TRYWAIT_HINT
+#define GPANN_TRYWAIT_HINT 0
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if GPANN_TRYWAIT_HINT > 0
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t) GPANN_TRYWAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
@@ -28,6 +41,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok;
 }
 __device__ __forceinline__ uint64_t global_timer_ns() {
@@ -38,10 +52,14 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+        if ((++spins & 0xFFu) == 0) {  // the clock is read once per 256 timed-out waits only
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

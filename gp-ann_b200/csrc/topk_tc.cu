@@ -38,6 +38,10 @@
 #include "params.h"
 #include "tc_ptx.cuh"
 
+#ifndef GPANN_SEL_SLEEP
+#define GPANN_SEL_SLEEP 1000
+#endif
+
 namespace gpann {
 namespace tc {
 
@@ -300,8 +304,8 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         const uint32_t avail = tail - head;
         if (avail == 0) {
             if (finished == (uint32_t) kEpiWarps) break;
-            if ((++idle & 31u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~10 us of idling
-            __nanosleep(200);
+            if ((++idle & 7u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~8 us of idling
+            __nanosleep(GPANN_SEL_SLEEP);  // an idle selection warp should cost (almost) no issue slots or power
             continue;
         }
         const uint32_t n = min(avail, 32u);
@@ -463,7 +467,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 tcgen05_fence_after();
                 for (int r = 0; r < R; ++r, ++it) {
                     const uint32_t slot = it & 1, sph = (it >> 1) & 1;
-                    mbar_wait(bar_tempty + 8 * slot, sph ^ 1);
+                    if (a.mode != 5) mbar_wait(bar_tempty + 8 * slot, sph ^ 1);  // probe 5: free-running MMA stream
                     tcgen05_fence_after();
                     const uint32_t dcol = tmem_base + slot * kTileN;
                     for (int ks = 0; ks < a.nks; ++ks) {
@@ -490,6 +494,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
         const int col_base = half * (kTileN / 2);
         uint32_t it = 0, slow_entries = 0;
+        // the selection warp that owns this warp's queries: (qs >> 5) & 1 = (4 r + wq) & 1 = wq & 1 for every r
+        const int sel = wq & (kSelWarps - 1);
+        Queue q;
+        q.cap = (uint32_t) a.qcap;
+        q.rec = s_qrec + sel * a.qcap;
+        q.tail = s_ctr + sel;
+        q.head = s_ctr + kSelWarps + sel;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
             const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
@@ -499,6 +510,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             // tile norm range (rows are sorted by norm): first and last row
             const int nmin_i = tn[0];
             const float nmin_f = __int_as_float(tn[0]), nmax_f = __int_as_float(tn[kTileN - 1]);
+            const float rmin_f = kFloat ? sqrtf(nmin_f) : 0.f, rmax_f = kFloat ? sqrtf(nmax_f) : 0.f;
             for (int r = 0; r < R; ++r, ++it) {
                 const uint32_t slot = it & 1, sph = (it >> 1) & 1;
                 const uint32_t qs = (uint32_t) (r * kTileM + qrow);
@@ -511,8 +523,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                     // g(nx) = nx - slack is evaluated at both ends of the tile's norm range (it is monotone in between)
                     const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
                     const float sq = 2.f * a.eps * sqrtf(nqv);
-                    const float g0 = nmin_f - sq * sqrtf(nmin_f) - 1e-5f * (nqv + nmin_f);
-                    const float g1 = nmax_f - sq * sqrtf(nmax_f) - 1e-5f * (nqv + nmax_f);
+                    const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
+                    const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
                     float gmin = fminf(g0, g1);
                     // g is a convex parabola in sqrt(nx) with its minimum at nx* = (eps^2)*nq: if the tile straddles it
                     // (points with norms far below the query's), use the global minimum instead of the end points
@@ -523,12 +535,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 } else {
                     Ti = (Uraw + nmin_i + 1) >> 1;
                 }
-                const int sel = (int) (qs >> 5) & (kSelWarps - 1);
-                Queue q;
-                q.cap = (uint32_t) a.qcap;
-                q.rec = s_qrec + sel * a.qcap;
-                q.tail = s_ctr + sel;
-                q.head = s_ctr + kSelWarps + sel;
+                if (a.mode == 5) continue;
                 mbar_wait(bar_tfull + 8 * slot, sph);
                 tcgen05_fence_after();
                 const uint32_t tbase = tmem_base + slot * kTileN + col_base + lane_sel;
