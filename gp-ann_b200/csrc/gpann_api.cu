@@ -460,6 +460,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
             a.ntiles = nsample;
             a.tile_stride = tiles_total / nsample;
             a.tile_lo = a.tile_stride / 2;
+            a.sample_pass = 1;
             launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
             GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
             TopkOut b;
@@ -471,6 +472,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.tile_lo = 0;
     a.tile_stride = 1;
     a.ntiles = tiles_total;
+    a.sample_pass = 0;
     static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
     if (want_stats) {
         GP_TRY(reserve(ctx, ctx->misc, 64));

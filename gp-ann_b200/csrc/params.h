@@ -116,6 +116,7 @@ struct Args {
     int d;
     uint32_t id_base;
     float eps;               // relative error bound of the bf16 dot product: |dot~ - dot| <= eps*|q|*|x|
+    int sample_pass;         // 1 for the strided pre-passes: their only product is an upper bound per query
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
 };
 

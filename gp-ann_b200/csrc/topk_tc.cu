@@ -92,7 +92,7 @@ __device__ __forceinline__ uint4 ld_shared_v4_volatile(const void* p) {
     return v;
 }
 
-__device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs) {
+__device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs, uint32_t extra = 0u) {
     const uint32_t pos = atomicAdd(q.tail, 1u);
     if (pos - *q.head >= q.cap) {  // full: wait for the selection warp (rare)
         const uint64_t t0 = global_timer_ns();
@@ -101,7 +101,7 @@ __device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t q
             if (global_timer_ns() - t0 > 4000000000ull) __trap();
         }
     }
-    st_shared_v4(q.rec + (pos & (q.cap - 1)), (uint32_t) key, (uint32_t) (key >> 32), qs, 0u);
+    st_shared_v4(q.rec + (pos & (q.cap - 1)), (uint32_t) key, (uint32_t) (key >> 32), qs, extra);
 }
 
 // v[j] for a run-time j without local memory: a 5-level tree of selects on the bits of j (31 SEL, depth 5).
@@ -144,10 +144,11 @@ __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, co
     }
 }
 
-// Float variant: the record carries the point id only (the approximate distance is not good enough to rank); the
-// selection warp recomputes the exact fp32 distance.
-__device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T, const uint32_t* ti, int col0, uint32_t qs,
-                                                const Queue& q) {
+// Float variant: the approximate distance is not good enough to rank, so the record carries the point id, the bf16
+// accumulator and the point's squared norm; the selection warp re-tests the candidate against the query's CURRENT k-th
+// distance (records age in the queue while the lists tighten) and only then recomputes the exact fp32 distance.
+__device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T, const int32_t* tn, const uint32_t* ti, int col0,
+                                                uint32_t qs, const Queue& q) {
     uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -161,7 +162,7 @@ __device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
         const uint32_t id = ti[col0 + j];
-        if (id != kInvalidId) queue_push(q, (uint64_t) id, qs);
+        if (id != kInvalidId) queue_push(q, ((uint64_t) pick32(v, j) << 32) | id, qs, (uint32_t) tn[col0 + j]);
     }
 }
 
@@ -183,6 +184,7 @@ struct SelState {
     const float* q_f32;     // this CTA's queries [nslots, d]
     int d;
     uint32_t id_base;
+    float eps;
 };
 
 // Squared L2 distance of two fp32 rows in the reference's summation order (src/dist.cpp:9-16 ->
@@ -257,9 +259,15 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
 }
 
 template <bool kFloat>
-__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key) {
-    if (kFloat) {  // the record holds the id: compute the exact distance now
+__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key, uint32_t extra) {
+    if (kFloat) {  // the record holds (accumulator, id) and the point's norm
         const uint32_t id = (uint32_t) key;
+        const uint64_t kth_now = s.kth[qs];
+        if (kth_now != kEmptyKey) {  // same test as the filter's, with this point's own norm and the current k-th distance
+            const float nqv = __int_as_float(s.nq[qs]), nx = __uint_as_float(extra), acc = __uint_as_float((uint32_t) (key >> 32));
+            const float lb = nqv + nx - 2.f * acc - (2.f * s.eps * sqrtf(nqv * nx) + 1e-5f * (nqv + nx));
+            if (lb - 1e-6f * fabsf(lb) > key_dist(kth_now)) return false;
+        }
         const float dist = exact_sqr_l2(s.rows_f32 + (size_t) (id - s.id_base) * s.d, s.q_f32 + (size_t) qs * s.d, s.d);
         key = pack_key(dist, id);
     }
@@ -311,6 +319,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         const uint32_t n = min(avail, 32u);
         uint32_t qs = 0xFFFF0000u + lane;  // unique dummy for idle lanes (never matches a real slot)
         uint64_t key = 0;
+        uint32_t extra = 0;
         bool pending = (uint32_t) lane < n;
         if (pending) {
             uint4* slot = q.rec + ((head + lane) & (q.cap - 1));
@@ -323,6 +332,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             }
             key = ((uint64_t) r.y << 32) | r.x;
             qs = r.z;
+            extra = r.w;
             reinterpret_cast<volatile uint32_t*>(slot)[2] = kQEmpty;
         }
         __threadfence_block();
@@ -334,7 +344,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             bool compact = false;
             if (pending && (__ffs(peers) - 1) == lane) {
-                compact = select_insert<kFloat>(s, qs, key);
+                compact = select_insert<kFloat>(s, qs, key, extra);
                 pending = false;
             }
             __syncwarp();
@@ -565,8 +575,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                             continue;
                         }
                         if (__any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
-                            if (ma >= Tf) enqueue_chunk_f(va, Tf, ti, col_base + c * 64, qs, q);
-                            if (mb >= Tf) enqueue_chunk_f(vb, Tf, ti, col_base + c * 64 + 32, qs, q);
+                            // cold lane of a SAMPLE pass (no bound yet): any subset of real distances bounds the k-th one,
+                            // so only the best value of each chunk goes to the selection warp instead of all 32
+                            const bool cold = a.sample_pass && Tf < -1.0e37f;
+                            if (ma >= Tf) enqueue_chunk_f(va, cold ? ma : Tf, tn, ti, col_base + c * 64, qs, q);
+                            if (mb >= Tf) enqueue_chunk_f(vb, cold ? mb : Tf, tn, ti, col_base + c * 64 + 32, qs, q);
                             __syncwarp();
                         }
                     } else {
@@ -577,8 +590,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                         }
                         if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
                             ++slow_entries;
-                            if (ma >= Ti) enqueue_chunk(va, Ti, tn, ti, col_base + c * 64, nqraw, qs, q);
-                            if (mb >= Ti) enqueue_chunk(vb, Ti, tn, ti, col_base + c * 64 + 32, nqraw, qs, q);
+                            const bool cold = a.sample_pass && Ti < -(1 << 28);  // see the float branch
+                            if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col_base + c * 64, nqraw, qs, q);
+                            if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col_base + c * 64 + 32, nqraw, qs, q);
                             __syncwarp();
                         }
                     }
@@ -612,6 +626,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.q_f32 = a.q_f32 ? a.q_f32 + qbase * a.d : nullptr;
         ss.d = a.d;
         ss.id_base = a.id_base;
+        ss.eps = a.eps;
         ss.gbound = a.bound ? a.bound + qbase : nullptr;
         ss.nslots = nslots;
         selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel);
