@@ -370,6 +370,13 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
     pl.max_r = pl.kblocks == 1 ? tc::kMaxR : 2;
     pl.stages = pl.kblocks == 1 ? 3 : 2;
     pl.qcap = pl.kblocks == 1 ? 1024 : 512;
+    // experiment knobs (probes; the defaults above are the tuned plan)
+    static const char* e_st = std::getenv("GPANN_TC_STAGES");
+    static const char* e_qc = std::getenv("GPANN_TC_QCAP");
+    static const char* e_r = std::getenv("GPANN_TC_R");
+    if (e_st) pl.stages = std::max(2, std::min(tc::kMaxStages, std::atoi(e_st)));
+    if (e_qc) pl.qcap = std::max(64, pow2_ceil(std::atoi(e_qc)));
+    if (e_r) pl.max_r = std::max(1, std::min(pl.max_r, std::atoi(e_r)));
     pl.nqb = nqb;
     pl.k = k;
     pl.R = (int) std::min<size_t>(pl.max_r, (nqb + tc::kTileM - 1) / tc::kTileM);  // Q tiles resident per CTA
@@ -426,6 +433,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.pnorm = lay.norms;
     a.pid = lay.ids;
     a.qnorm = ctx->qnorm.p;
+    a.qrows = (const unsigned char*) ctx->qrows.p;
     a.R = pl.R;
     a.G = pl.G;
     a.S = S;
@@ -475,8 +483,8 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.sample_pass = 0;
     static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
     if (want_stats) {
-        GP_TRY(reserve(ctx, ctx->misc, 64));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 16, st));
+        GP_TRY(reserve(ctx, ctx->misc, 128));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 128, st));
         a.stats = (unsigned long long*) ctx->misc.p;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
@@ -487,10 +495,15 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     }
     GP_TRY(check_launch(ctx, "topk_tc_kernel"));
     if (want_stats) {
-        unsigned long long h[2] = { 0, 0 };
+        unsigned long long h[16] = { 0 };
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, ctx->misc.p, 16, cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u\n", h[0], h[1], grid);
+        cudaMemcpy(h, ctx->misc.p, 128, cudaMemcpyDeviceToHost);
+        const double g = (double) grid, items = (double) tiles_total / S * pl.R * tc::kHalves;
+        std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u, %.0f items/CTA\n", h[0], h[1], grid, items);
+        std::fprintf(stderr, "[gpann stats] clk per item (CTA average): MMA thread total %.0f = wait operands %.0f + wait TMEM slot %.0f + issue %.0f | "
+                             "filter warp 0 total %.0f = wait accumulator %.0f + wait tile %.0f + work %.0f | TMA thread total %.0f, wait free stage %.0f\n",
+                     h[2] / g / items, h[3] / g / items, h[4] / g / items, (h[2] - h[3] - h[4]) / g / items, h[5] / g / items, h[6] / g / items,
+                     h[7] / g / items, (h[5] - h[6] - h[7]) / g / items, h[9] / g / items, h[8] / g / items);
     }
     if (!carry) {
         if (ctx->tc_warm) {  // probe: the final k-th distances become the next call's bounds

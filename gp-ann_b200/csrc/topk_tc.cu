@@ -366,10 +366,29 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
     }
 }
 
+// One tcgen05.mma of an item: A = query tile (shared-memory descriptor, or TMEM columns when kATmem), B = point tile.
 template <bool kFloat>
+__device__ __forceinline__ void issue_mma(uint32_t dcol, uint64_t adesc, uint64_t bdesc, int a_tmem_col, uint32_t tmem_base,
+                                          uint32_t idesc, bool accumulate) {
+    if (kATmem) {
+        const uint32_t acol = tmem_base + kATmemCol + (uint32_t) a_tmem_col;
+        if (kFloat) umma_bf16_ts(dcol, acol, bdesc, idesc, accumulate ? 1u : 0u);
+        else umma_i8_ts(dcol, acol, bdesc, idesc, accumulate ? 1u : 0u);
+    } else {
+        if (kFloat) umma_bf16(dcol, adesc, bdesc, idesc, accumulate ? 1u : 0u);
+        else umma_i8(dcol, adesc, bdesc, idesc, accumulate ? 1u : 0u);
+    }
+}
+
+// kProbe = false is the production instantiation: the probe modes (Args::mode) and the diagnostics (Args::stats) are
+// compiled out, because every uniform load + compare + branch they cost sits on the per-item critical path of the
+// single MMA-issuing thread and of the filter warps (ncu: ~190 instructions per item in the issuer alone before).
+template <bool kFloat, bool kProbe>
 __global__ void __launch_bounds__(kThreads, 1)
 topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q, const Args a) {
     extern __shared__ unsigned char smem_raw[];
+    const int mode = kProbe ? a.mode : 0;
+    unsigned long long* const stats = kProbe ? a.stats : nullptr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = a.R, KB = a.kblocks, NST = a.stages;
     const int g = blockIdx.x % a.G, s = blockIdx.x / a.G;
@@ -385,10 +404,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     const uint32_t sQ = raw_addr + pad;
     const uint32_t sP = sQ + R * q_tile_bytes;
     unsigned char* after = base + (size_t) R * q_tile_bytes + (size_t) NST * p_tile_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(after);  // full[3], empty[3], qfull, tfull[2], tempty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(after);  // full[3], empty[3], qfull, tfull[kSlots], tempty[kSlots]
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages, bar_q = bar_empty + 8 * kMaxStages,
-                   bar_tfull = bar_q + 8, bar_tempty = bar_tfull + 16;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 8 * (2 * kMaxStages + 5));
+                   bar_tfull = bar_q + 8, bar_tempty = bar_tfull + 8 * kSlots;
+    static_assert(8 * (2 * kMaxStages + 1 + 2 * kSlots) <= 124, "barrier area");
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 124);
     uint32_t* s_ctr = reinterpret_cast<uint32_t*>(after + 128);               // q_tail[2], q_head[2], done
     int32_t* s_norm = reinterpret_cast<int32_t*>(after + 256);                 // [NST][256] int32 or float bits
     uint32_t* s_id = reinterpret_cast<uint32_t*>(s_norm + NST * kTileN);       // [NST][256]
@@ -419,21 +439,21 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     }
     for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qrec[i] = make_uint4(0u, 0u, kQEmpty, 0u);
     if (tid < 8) s_ctr[tid] = 0;
-    if (warp == 0 && lane == 0) {
+    if (warp == kTmaWarp && lane == 0) {
         prefetch_tmap(&tmap_p);
         prefetch_tmap(&tmap_q);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1 + kEpiWarps);  // MMA commit + every filter warp done with the tile
         }
-        mbar_init(bar_q, 1);
-        for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_q, kATmem ? kEpiWarps : 1);
+        for (int i = 0; i < kSlots; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, kEpiWarps);  // one arrive per filter warp
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                      "r"((uint32_t) kTmemCols)
                      : "memory");
@@ -446,64 +466,139 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     uint64_t* my_lists = a.cand + (size_t) blockIdx.x * nslots * a.cap;
     const int kb_elems = kFloat ? 64 : 128;  // elements per 128-byte K block
 
-    if (warp == 0) {
+    if (kATmem && warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps) {
+        // Query tiles -> tensor memory, once: lane = query row, 32 columns per 128-byte K block (bytes of the row in
+        // order), which is the layout tcgen05.mma expects for an A operand in TMEM.  Warp (w & 3) may touch TMEM lanes
+        // [32*(w&3), +32) only; the two column-half groups of filter warps split the R tiles.
+        const int wq = warp & 3;
+        for (int r = (warp - kFilterWarp0) >> 2; r < R; r += kEpiWarps / 4) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.qrows + ((size_t) (g * R + r) * kTileM + wq * 32 + lane) * ((size_t) KB * kRowBytes));
+            for (int kb = 0; kb < KB; ++kb) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 x = __ldg(src + kb * 8 + i);
+                    v[4 * i] = x.x, v[4 * i + 1] = x.y, v[4 * i + 2] = x.z, v[4 * i + 3] = x.w;
+                }
+                tmem_st32(tmem_base + kATmemCol + (r * KB + kb) * 32 + ((uint32_t) (wq * 32) << 16), v);
+            }
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_q);
+    }
+
+    if (warp == kTmaWarp) {
         if (lane == 0) {
             // ===== TMA producer =====
-            mbar_expect_tx(bar_q, (uint32_t) R * q_tile_bytes);
-            for (int r = 0; r < R; ++r)
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(sQ + r * q_tile_bytes + kb * kQBlockBytes, &tmap_q, bar_q, kb * kb_elems, (int) ((g * R + r) * kTileM));
-            for (uint32_t t = tile_begin; t < tile_end; ++t) {
-                const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
+            if (!kATmem) {
+                mbar_expect_tx(bar_q, (uint32_t) R * q_tile_bytes);
+                for (int r = 0; r < R; ++r)
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_2d(sQ + r * q_tile_bytes + kb * kQBlockBytes, &tmap_q, bar_q, kb * kb_elems, (int) ((g * R + r) * kTileM));
+            }
+            long long w_empty = 0;
+            const long long t_begin = stats ? clock64() : 0;
+            uint32_t st = 0, ph = 0;
+            size_t row0 = ((size_t) a.tile_lo + (size_t) tile_begin * a.tile_stride) * kTileN;
+            const size_t row_step = (size_t) a.tile_stride * kTileN;
+            for (uint32_t t = tile_begin; t < tile_end; ++t, row0 += row_step) {
+                const long long c0 = stats ? clock64() : 0;
                 mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                if (stats) w_empty += clock64() - c0;
                 mbar_expect_tx(bar_full + 8 * st, p_tile_bytes + 2 * kTileN * 4);
-                const size_t row0 = ((size_t) a.tile_lo + (size_t) t * a.tile_stride) * kTileN;
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_2d(sP + st * p_tile_bytes + kb * kPBlockBytes, &tmap_p, bar_full + 8 * st, kb * kb_elems, (int) row0);
                 bulk_load_1d(smem_u32(s_norm + st * kTileN), reinterpret_cast<const int32_t*>(a.pnorm) + row0, kTileN * 4,
                              bar_full + 8 * st);
                 bulk_load_1d(smem_u32(s_id + st * kTileN), a.pid + row0, kTileN * 4, bar_full + 8 * st);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            mbar_wait(bar_q, 0);
-            tcgen05_fence_after();
-            uint32_t it = 0;
-            for (uint32_t t = tile_begin; t < tile_end; ++t) {
-                const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
-                mbar_wait(bar_full + 8 * st, ph);
-                tcgen05_fence_after();
-                for (int r = 0; r < R; ++r, ++it) {
-                    const uint32_t slot = it & 1, sph = (it >> 1) & 1;
-                    if (a.mode != 5) mbar_wait(bar_tempty + 8 * slot, sph ^ 1);  // probe 5: free-running MMA stream
-                    tcgen05_fence_after();
-                    const uint32_t dcol = tmem_base + slot * kTileN;
-                    for (int ks = 0; ks < a.nks; ++ks) {
-                        // K step ks = 32 bytes: block ks/4 of the row, +2 (16-byte units) per step inside the block
-                        const int kb = ks >> 2, w = ks & 3;
-                        const uint64_t adesc = make_sw128_desc(sQ + r * q_tile_bytes + kb * kQBlockBytes) + 2 * w;
-                        const uint64_t bdesc = make_sw128_desc(sP + st * p_tile_bytes + kb * kPBlockBytes) + 2 * w;
-                        if (a.mode == 3) continue;  // probe: no MMA at all, the drain rate alone
-                        if (kFloat) umma_bf16(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
-                        else umma_i8(dcol, adesc, bdesc, a.idesc, ks > 0 ? 1u : 0u);
-                    }
-                    umma_commit(bar_tfull + 8 * slot);  // accumulator ready for the filter warps
+                if (++st == (uint32_t) NST) {
+                    st = 0;
+                    ph ^= 1;
                 }
-                umma_commit(bar_empty + 8 * st);  // operands consumed (1 of 1+kEpiWarps arrivals)
+            }
+            if (stats) {
+                atomicAdd(stats + 8, (unsigned long long) w_empty);
+                atomicAdd(stats + 9, (unsigned long long) (clock64() - t_begin));
             }
         }
-    } else if (warp < 2 + kEpiWarps) {
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer: the whole warp walks the loop (so its control flow stays warp-uniform), one elected lane
+        // issues the tcgen05.mma / tcgen05.commit of an item.  Shared-memory descriptors differ from a base descriptor
+        // only in the 14-bit start-address field, so every operand descriptor is base + a small constant.
+        mbar_wait(bar_q, 0);
+        tcgen05_fence_after();
+        const uint64_t a_base = make_sw128_desc(sQ), b_base = make_sw128_desc(sP);
+        const uint32_t idesc = a.idesc;
+        const int nks = a.nks;
+        uint32_t st = 0, ph = 0, slot = 0, sph = 0;
+        long long w_full = 0, w_tempty = 0;
+        const long long t_begin = stats ? clock64() : 0;
+        for (uint32_t t = tile_begin; t < tile_end; ++t) {
+            const long long c0 = stats ? clock64() : 0;
+            mbar_wait(bar_full + 8 * st, ph);
+            if (stats) w_full += clock64() - c0;
+            tcgen05_fence_after();
+            const uint64_t b_st = b_base + ((st * p_tile_bytes) >> 4);
+            for (int r = 0; r < R; ++r) {
+                const uint64_t a_r = a_base + (((uint32_t) r * q_tile_bytes) >> 4);
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h) {
+                    const long long c1 = stats ? clock64() : 0;
+                    if (mode != 5) mbar_wait(bar_tempty + 8 * slot, sph ^ 1);  // probe 5: free-running MMA stream
+                    if (stats) w_tempty += clock64() - c1;
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t dcol = tmem_base + slot * kAccN;
+                        // K step ks = 32 bytes: block ks/4 of the row, +2 (16-byte units) per step inside the block;
+                        // rows [h*kAccN, +kAccN) of the point tile start h*kAccN*128 bytes into each K block
+                        const uint64_t b_h = b_st + (uint32_t) (h * ((kAccN * kRowBytes) >> 4));
+                        if (mode != 3) {  // probe 3: no MMA at all, the drain rate alone
+                            if (nks == 4) {  // d = 128 bytes / 64 bf16: one K block, fully unrolled
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) issue_mma<kFloat>(dcol, a_r + 2 * ks, b_h + 2 * ks, r * KB * 32 + 8 * ks, tmem_base, idesc, ks > 0);
+                            } else {
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    const int kb = ks >> 2, w = ks & 3;
+                                    issue_mma<kFloat>(dcol, a_r + (uint32_t) (kb * (kQBlockBytes >> 4) + 2 * w),
+                                                      b_h + (uint32_t) (kb * (kPBlockBytes >> 4) + 2 * w), r * KB * 32 + 8 * ks, tmem_base, idesc, ks > 0);
+                                }
+                            }
+                        }
+                        umma_commit(bar_tfull + 8 * slot);  // accumulator ready for the filter warps
+                    }
+                    __syncwarp();
+                    if (++slot == (uint32_t) kSlots) {
+                        slot = 0;
+                        sph ^= 1;
+                    }
+                }
+            }
+            if (elect_one()) umma_commit(bar_empty + 8 * st);  // operands consumed (1 of 1+kEpiWarps arrivals)
+            __syncwarp();
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        if (stats && lane == 0) {
+            atomicAdd(stats + 2, (unsigned long long) (clock64() - t_begin));
+            atomicAdd(stats + 3, (unsigned long long) w_full);
+            atomicAdd(stats + 4, (unsigned long long) w_tempty);
+        }
+    } else if (warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps) {
         // ===== filter: every warp drains every item; warp (w & 3) owns TMEM lanes [32*(w&3), +32) and the column
         // half (w-2)/4 of the 256-column accumulator =====
-        const int ew = warp - 2;
-        const int half = ew >> 2;
+        const int ew = warp - kFilterWarp0;
+        const int half = ew >> 2;  // column group of this warp: kEpiWarps/4 groups of kColsPerWarp columns
         const int wq = warp & 3;
         const int qrow = wq * 32 + lane;
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
-        const int col_base = half * (kTileN / 2);
-        uint32_t it = 0, slow_entries = 0;
+        constexpr int kColsPerWarp = kAccN / (kEpiWarps / 4);
+        static_assert(kColsPerWarp % 64 == 0, "a filter warp drains 64 columns at a time");
+        const int col_base = half * kColsPerWarp;  // this warp's columns inside an accumulator
+        uint32_t slow_entries = 0;
         // the selection warp that owns this warp's queries: (qs >> 5) & 1 = (4 r + wq) & 1 = wq & 1 for every r
         const int sel = wq & (kSelWarps - 1);
         Queue q;
@@ -511,103 +606,140 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         q.rec = s_qrec + sel * a.qcap;
         q.tail = s_ctr + sel;
         q.head = s_ctr + kSelWarps + sel;
+        long long w_tfull = 0, w_pfull = 0;
+        const long long t_begin = stats ? clock64() : 0;
+        uint32_t st = 0, ph = 0, slot = 0, sph = 0;
+        const uint32_t tbase0 = tmem_base + col_base + lane_sel;
+        const int sample_pass = a.sample_pass;
+        const float eps = a.eps;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
-            const uint32_t tl = t - tile_begin, st = tl % NST, ph = (tl / NST) & 1;
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
+            const long long c0 = stats ? clock64() : 0;
             mbar_wait(bar_full + 8 * st, ph);
+            if (stats) w_pfull += clock64() - c0;
             const int32_t* tn = s_norm + st * kTileN;
             const uint32_t* ti = s_id + st * kTileN;
-            // tile norm range (rows are sorted by norm): first and last row
-            const int nmin_i = tn[0];
-            const float nmin_f = __int_as_float(tn[0]), nmax_f = __int_as_float(tn[kTileN - 1]);
-            const float rmin_f = kFloat ? sqrtf(nmin_f) : 0.f, rmax_f = kFloat ? sqrtf(nmax_f) : 0.f;
-            for (int r = 0; r < R; ++r, ++it) {
-                const uint32_t slot = it & 1, sph = (it >> 1) & 1;
+            // norm range of each item's rows (rows are sorted by norm): first and last row
+            int nmin_i[kHalves];
+            float nmin_fa[kHalves], nmax_fa[kHalves], rmin_fa[kHalves], rmax_fa[kHalves];
+#pragma unroll
+            for (int h = 0; h < kHalves; ++h) {
+                nmin_i[h] = tn[h * kAccN];
+                nmin_fa[h] = __int_as_float(tn[h * kAccN]);
+                nmax_fa[h] = __int_as_float(tn[h * kAccN + kAccN - 1]);
+                rmin_fa[h] = kFloat ? sqrtf(nmin_fa[h]) : 0.f;
+                rmax_fa[h] = kFloat ? sqrtf(nmax_fa[h]) : 0.f;
+            }
+            for (int r = 0; r < R; ++r) {
                 const uint32_t qs = (uint32_t) (r * kTileM + qrow);
                 const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
                 const int nqraw = s_nq[qs];
-                int Ti = 0;
-                float Tf = 0.f;
-                if (kFloat) {
-                    // keep x if  nq + nx - 2*dot~ - slack(nq,nx) <= kth,  slack = 2*eps*sqrt(nq*nx) + 1e-5*(nq+nx);
-                    // g(nx) = nx - slack is evaluated at both ends of the tile's norm range (it is monotone in between)
-                    const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
-                    const float sq = 2.f * a.eps * sqrtf(nqv);
-                    const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
-                    const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
-                    float gmin = fminf(g0, g1);
-                    // g is a convex parabola in sqrt(nx) with its minimum at nx* = (eps^2)*nq: if the tile straddles it
-                    // (points with norms far below the query's), use the global minimum instead of the end points
-                    const float nstar = a.eps * a.eps * nqv;
-                    if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
-                    Tf = 0.5f * (U + gmin);
-                    Tf -= 1e-6f * fabsf(Tf);
-                } else {
-                    Ti = (Uraw + nmin_i + 1) >> 1;
-                }
-                if (a.mode == 5) continue;
-                mbar_wait(bar_tfull + 8 * slot, sph);
-                tcgen05_fence_after();
-                const uint32_t tbase = tmem_base + slot * kTileN + col_base + lane_sel;
-                if (a.mode == 2) {  // probe: MMA issue rate only
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
-                    continue;
-                }
-                // 128 columns per warp and item, 64 at a time.  (Draining all 128 first and releasing the slot early
-                // was measured slower: the drain is bound by the TMEM read path, 128 KB per item ~ 256 B/clk/SM.)
-#pragma unroll 1
-                for (int c = 0; c < kTileN / 128; ++c) {
-                    uint32_t va[32], vb[32];
-                    tmem_ld32(tbase + c * 64, va);
-                    tmem_ld32(tbase + c * 64 + 32, vb);
-                    tmem_wait_ld();
-                    if (c == kTileN / 128 - 1) {  // accumulator drained into registers: hand the slot back before the
-                        tcgen05_fence_before();   // arithmetic, so a slow-path entry on this half cannot stall the MMA
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h) {
+                    const uint32_t bar_tf = bar_tfull + 8 * slot, bar_te = bar_tempty + 8 * slot, par_tf = sph;
+                    const uint32_t tbase = tbase0 + slot * kAccN;
+                    if (++slot == (uint32_t) kSlots) {
+                        slot = 0;
+                        sph ^= 1;
                     }
+                    const int row0 = h * kAccN;  // first tile row of this item
+                    int Ti = 0;
+                    float Tf = 0.f;
                     if (kFloat) {
-                        const float ma = max32f(va), mb = max32f(vb);
-                        if (a.mode == 1 || a.mode == 3) {
-                            if (fmaxf(ma, mb) == 3.0e38f) s_U[qs] = __float_as_int(ma);
-                            continue;
-                        }
-                        if (__any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
-                            // cold lane of a SAMPLE pass (no bound yet): any subset of real distances bounds the k-th one,
-                            // so only the best value of each chunk goes to the selection warp instead of all 32
-                            const bool cold = a.sample_pass && Tf < -1.0e37f;
-                            if (ma >= Tf) enqueue_chunk_f(va, cold ? ma : Tf, tn, ti, col_base + c * 64, qs, q);
-                            if (mb >= Tf) enqueue_chunk_f(vb, cold ? mb : Tf, tn, ti, col_base + c * 64 + 32, qs, q);
-                            __syncwarp();
-                        }
+                        // keep x if  nq + nx - 2*dot~ - slack(nq,nx) <= kth,  slack = 2*eps*sqrt(nq*nx) + 1e-5*(nq+nx);
+                        // g(nx) = nx - slack is evaluated at both ends of the item's norm range (it is monotone in between)
+                        const float nmin_f = nmin_fa[h], nmax_f = nmax_fa[h], rmin_f = rmin_fa[h], rmax_f = rmax_fa[h];
+                        const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
+                        const float sq = 2.f * eps * sqrtf(nqv);
+                        const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
+                        const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
+                        float gmin = fminf(g0, g1);
+                        // g is a convex parabola in sqrt(nx) with its minimum at nx* = (eps^2)*nq: if the item straddles it
+                        // (points with norms far below the query's), use the global minimum instead of the end points
+                        const float nstar = eps * eps * nqv;
+                        if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
+                        Tf = 0.5f * (U + gmin);
+                        Tf -= 1e-6f * fabsf(Tf);
                     } else {
-                        const int ma = max32(va), mb = max32(vb);
-                        if (a.mode == 1 || a.mode == 3) {  // probe: keep the loads and the max alive, skip selection
-                            if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
-                            continue;
-                        }
-                        if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
-                            ++slow_entries;
-                            const bool cold = a.sample_pass && Ti < -(1 << 28);  // see the float branch
-                            if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col_base + c * 64, nqraw, qs, q);
-                            if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col_base + c * 64 + 32, nqraw, qs, q);
+                        Ti = (Uraw + nmin_i[h] + 1) >> 1;
+                    }
+                    if (mode == 5) continue;
+                    const long long c1 = stats ? clock64() : 0;
+                    mbar_wait(bar_tf, par_tf);
+                    if (stats) w_tfull += clock64() - c1;
+                    tcgen05_fence_after();
+                    if (mode == 2) {  // probe: MMA issue rate only
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_te);
+                        continue;
+                    }
+                    // kColsPerWarp columns per warp and item, 64 at a time (two x32 loads in flight).  A software pipeline
+                    // of single x32 loads (next chunk in flight during the max tree) was measured SLOWER (120 -> 135 ms):
+                    // the TMEM read path is not the limit (~1 KB/clk/SM, profiles/tools/tmem_ld_bench.cu); what matters is
+                    // how soon after tcgen05.commit the slot goes back to the MMA issuer.
+#pragma unroll
+                    for (int c = 0; c < kColsPerWarp / 64; ++c) {
+                        uint32_t va[32], vb[32];
+                        tmem_ld32(tbase + c * 64, va);
+                        tmem_ld32(tbase + c * 64 + 32, vb);
+                        tmem_wait_ld();
+                        if (c == kColsPerWarp / 64 - 1) {  // accumulator drained into registers: hand the slot back before the
+                            tcgen05_fence_before();        // arithmetic, so a slow-path entry on this half cannot stall the MMA
                             __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_te);
+                        }
+                        const int col0 = row0 + col_base + c * 64;  // tile row of va[0]
+                        if (kFloat) {
+                            const float ma = max32f(va), mb = max32f(vb);
+                            if (mode == 1 || mode == 3) {  // probe: keep the loads and the max alive, skip selection
+                                if (fmaxf(ma, mb) == 3.0e38f) s_U[qs] = __float_as_int(ma);
+                                continue;
+                            }
+                            if (__any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
+                                // cold lane of a SAMPLE pass (no bound yet): any subset of real distances bounds the k-th one,
+                                // so only the best value of each chunk goes to the selection warp instead of all 32
+                                const bool cold = sample_pass && Tf < -1.0e37f;
+                                if (ma >= Tf) enqueue_chunk_f(va, cold ? ma : Tf, tn, ti, col0, qs, q);
+                                if (mb >= Tf) enqueue_chunk_f(vb, cold ? mb : Tf, tn, ti, col0 + 32, qs, q);
+                                __syncwarp();
+                            }
+                        } else {
+                            const int ma = max32(va), mb = max32(vb);
+                            if (mode == 1 || mode == 3) {
+                                if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
+                                continue;
+                            }
+                            if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
+                                ++slow_entries;
+                                const bool cold = sample_pass && Ti < -(1 << 28);  // see the float branch
+                                if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col0, nqraw, qs, q);
+                                if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col0 + 32, nqraw, qs, q);
+                                __syncwarp();
+                            }
                         }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms/ids
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
         }
         __threadfence_block();
         __syncwarp();
-        if (a.stats && lane == 0) atomicAdd(a.stats + 1, (unsigned long long) slow_entries);
+        if (stats && lane == 0) atomicAdd(stats + 1, (unsigned long long) slow_entries);
+        if (stats && lane == 0 && ew == 0) {
+            atomicAdd(stats + 5, (unsigned long long) (clock64() - t_begin));
+            atomicAdd(stats + 6, (unsigned long long) w_tfull);
+            atomicAdd(stats + 7, (unsigned long long) w_pfull);
+        }
         if (lane == 0) atomicAdd(s_ctr + 2 * kSelWarps, 1u);  // done: every record of this warp is in a queue
     } else {
         // ===== selection warps: exact per-query top-k lists, thresholds published through s_U =====
-        const int sel = warp - (2 + kEpiWarps);
+        const int sel = warp - kSelWarp0;
         Queue q;
         q.cap = (uint32_t) a.qcap;
         q.rec = s_qrec + sel * a.qcap;
@@ -630,13 +762,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.gbound = a.bound ? a.bound + qbase : nullptr;
         ss.nslots = nslots;
         selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel);
-        if (a.stats && lane == 0) atomicAdd(a.stats, (unsigned long long) *q.tail);  // records pushed to this queue
+        if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
     }
 
     // ---- final selection: every query's k best of this CTA's point range -> partial[s], by all non-role warps ----
-    if (warp >= 2) {
+    if (warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps + kSelWarps) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + kSelWarps)) : "memory");
-        for (int qs = warp - 2; qs < nslots; qs += kEpiWarps + kSelWarps) {
+        for (int qs = warp - kFilterWarp0; qs < nslots; qs += kEpiWarps + kSelWarps) {
             const uint64_t* b = my_lists + (size_t) qs * a.cap;
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
             const int cnt = s_cnt[qs];
@@ -646,7 +778,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols)
                      : "memory");
@@ -657,15 +789,23 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
 
 cudaError_t tc_set_attributes() {
     const int big = 227 * 1024;
-    cudaError_t e = cudaFuncSetAttribute(tc::topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaError_t e = cudaFuncSetAttribute(tc::topk_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::topk_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::topk_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::topk_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     return e;
 }
 
 void launch_topk_tc(bool is_float, const CUtensorMap& tmap_p, const CUtensorMap& tmap_q, const tc::Args& a, unsigned grid,
                     size_t smem, cudaStream_t st) {
-    if (is_float) tc::topk_tc_kernel<true><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
-    else tc::topk_tc_kernel<false><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+    const bool probe = a.mode != 0 || a.stats != nullptr;  // GPANN_TC_MODE / GPANN_TC_STATS: the instrumented instantiation
+    if (is_float) {
+        if (probe) tc::topk_tc_kernel<true, true><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+        else tc::topk_tc_kernel<true, false><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+    } else {
+        if (probe) tc::topk_tc_kernel<false, true><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+        else tc::topk_tc_kernel<false, false><<<grid, tc::kThreads, smem, st>>>(tmap_p, tmap_q, a);
+    }
 }
 
 }  // namespace gpann
