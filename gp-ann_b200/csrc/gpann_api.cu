@@ -45,6 +45,7 @@ struct gpann_ctx {
     bool timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // grow-only scratch, reused across calls (a ctx is externally synchronised)
+    DevBuf pace;
     DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
         sort_d, segsums, cent, sums, counts, assign, km_cent, km_hn, km_scal, km_partial, km_amb_list, km_amb_info;
     int km_mode = 0;     // GPANN_KM_MODE env: 2 = probe (MMA issue only, results invalid)
@@ -481,6 +482,12 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.tile_stride = 1;
     a.ntiles = tiles_total;
     a.sample_pass = 0;
+    static const bool no_pace = std::getenv("GPANN_TC_NOPACE") != nullptr;
+    if (!no_pace && tiles_total / S >= 4 * tc::kPaceWindow && pl.G > 1 && (int) grid <= ctx->num_sms) {  // all CTAs co-resident
+        GP_TRY(reserve(ctx, ctx->pace, (size_t) grid * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->pace.p, 0, (size_t) grid * sizeof(uint32_t), st));
+        a.pace = (uint32_t*) ctx->pace.p;
+    }
     static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
     if (want_stats) {
         GP_TRY(reserve(ctx, ctx->misc, 128));
@@ -1051,7 +1058,7 @@ void gpann_destroy(gpann_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
+    DevBuf* bufs[] = { &ctx->pace, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
                        &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info };

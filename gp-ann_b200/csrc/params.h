@@ -105,6 +105,7 @@ constexpr int kFilterWarp0 = GPANN_ROLES_HI ? 0 : 2;  // filter warp w owns TMEM
 constexpr int kSelWarp0 = kFilterWarp0 + kEpiWarps;
 constexpr int kQBlockBytes = kTileM * kRowBytes;  // 16 KB per K block of a query tile
 constexpr int kPBlockBytes = kTileN * kRowBytes;  // 32 KB per K block of a point tile
+constexpr uint32_t kPaceWindow = 192;            // tiles a CTA may run ahead of the slowest CTA of its point split
 constexpr int kTmemCols = 512;                   // accumulator slots (+ the resident query tiles when kATmem)
 // Pipeline shape (compile-time, A/B-tested through GPANN_NVCC_EXTRA): an "item" is one MMA accumulator of 128 queries x
 // kAccN points; kSlots accumulators rotate through TMEM; with kATmem the query tiles (operand A) live in TMEM columns
@@ -149,6 +150,7 @@ struct Args {
     uint32_t id_base;
     float eps;               // relative error bound of the bf16 dot product: |dot~ - dot| <= eps*|q|*|x|
     int sample_pass;         // 1 for the strided pre-passes: their only product is an upper bound per query
+    uint32_t* pace;          // optional [S*G] tile positions of the CTAs (zeroed before the launch): L2 pacing of a split's CTAs
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
 };
 
