@@ -44,6 +44,26 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+# MEASURED_PEAKS.json has no int8 figure.  The denominator of the tensor roofline is this repo's own measurement of the
+# tensor pipe on this pool's B200s: profiles/tools/mma_issue_bench.cu issues back-to-back tcgen05.mma.kind::i8
+# (M128 N256 K32, random operands, no loads, no epilogue) on all 148 SMs for ~150 ms and sustains 4.18-4.21 POP/s under
+# the 1000 W cap (4.56 POP/s for a 5 ms burst = the nominal 8192 MAC/clk/SM); profiles/r1_mma_issue_bench.txt.
+I8_TOPS_SUSTAINED = 4200.0
+
+
+def measured_traffic(n_rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE main-pass launch from the committed ncu capture
+    (profiles/r1_traffic.json), if it was taken at this shard size."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        t = json.load(open(path))
+        if int(t["rows"]) == int(n_rows):
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -292,9 +312,8 @@ def main():
         kms = statistics.mean(kernel_ms)
         ops_per_launch = 2.0 * D * n_local * NQ  # 2*d ops per distance evaluation
         achieved = ops_per_launch / (kms * 1e-3) / 1e12
-        # no int8 figure in MEASURED_PEAKS.json: the interim denominator is 2x the measured dense bf16 rate
-        # (int8 tcgen05 issues twice the MACs per instruction); sustained, because the kernel runs ~0.1 s per launch
-        peak = 2.0 * pk["bf16_tflops_sustained"]
+        peak = I8_TOPS_SUSTAINED
+        peak_bf16x2 = 2.0 * pk["bf16_tflops_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -303,9 +322,13 @@ def main():
                        "l2": "inputs (12.8 GB of points per pass) exceed the 126 MB L2; no flush needed"},
             "queries_per_s": value / N_TOTAL,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "topk_tc_kernel<false>", "kernel_ms": kms,
-                         "peak_source": f"2 x bf16_tflops_sustained ({pk_src} MEASURED_PEAKS.json; no int8 peak measured)",
+                         "traffic": measured_traffic(n_local), "kernel": "topk_tc_kernel<false,false>", "kernel_ms": kms,
+                         "peak_source": "own measurement: sustained tcgen05.mma.kind::i8 issue-only rate, all SMs, ~150 ms under the "
+                                        "power cap (profiles/tools/mma_issue_bench.cu); MEASURED_PEAKS.json has no int8 figure",
+                         "frac_of_2x_bf16_sustained": achieved / peak_bf16x2,
+                         "peak_2x_bf16_sustained": peak_bf16x2, "bf16_peak_source": pk_src,
                          "algorithmic_ops_per_launch": ops_per_launch,
+                         "algorithmic_bytes_per_launch": n_local * (D + 8),
                          "hbm_gbs_achieved": n_local * (D + 8) / (kms * 1e-3) / 1e9},
             "clocks": clocks, "gpu_launches": int(launches * world),
         }

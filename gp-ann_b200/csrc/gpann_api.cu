@@ -462,16 +462,34 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     // tiny), then 12 and 160 tiles per split, each filtered by the previous level's bound.  (During a pass the CTAs of
     // different point splits also share their k-th distances through a.bound, see publish_threshold.)
     if (prepass && ctx->tc_prepass && ctx->tc_mode == 0 && !(ctx->tc_warm && ctx->tc_warm_valid)) {
-        const uint32_t levels[3] = { 1, 12, 160 };
+        uint32_t levels[3] = { 1, 12, 160 };
+        static const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment knob: "a/b/c" tiles per split (0 = skip the level)
+        if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
         for (uint32_t per_split : levels) {
+            if (per_split == 0) continue;
             const uint32_t nsample = (uint32_t) S * per_split;
             if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
             a.ntiles = nsample;
             a.tile_stride = tiles_total / nsample;
             a.tile_lo = a.tile_stride / 2;
             a.sample_pass = 1;
+            static const char* e_sst = std::getenv("GPANN_TC_STATS");
+            if (e_sst && std::atoi(e_sst) >= 2) {
+                GP_TRY(reserve(ctx, ctx->misc, 256));
+                CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
+                a.stats = (unsigned long long*) ctx->misc.p;
+            }
             launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
             GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
+            if (a.stats) {
+                unsigned long long h[32] = { 0 };
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
+                std::fprintf(stderr, "[gpann stats] sample pass %u tiles/split: CTA 0 clk: filter loop done %llu, selection drained %llu, final selection done %llu; "
+                                     "records %llu; mma thread clk %llu | CTA 0 selection warp 0: %llu batches, %llu rounds, insert clk %llu, pop clk %llu, idle polls %llu\n",
+                             per_split, h[10], h[11], h[12], h[0], h[2] / grid, h[16], h[17], h[18], h[20], h[19]);
+                a.stats = nullptr;
+            }
             TopkOut b;
             b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
             b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
@@ -490,8 +508,8 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     }
     static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
     if (want_stats) {
-        GP_TRY(reserve(ctx, ctx->misc, 128));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 128, st));
+        GP_TRY(reserve(ctx, ctx->misc, 256));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
         a.stats = (unsigned long long*) ctx->misc.p;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
@@ -502,9 +520,9 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     }
     GP_TRY(check_launch(ctx, "topk_tc_kernel"));
     if (want_stats) {
-        unsigned long long h[16] = { 0 };
+        unsigned long long h[32] = { 0 };
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, ctx->misc.p, 128, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
         const double g = (double) grid, items = (double) tiles_total / S * pl.R * tc::kHalves;
         std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u, %.0f items/CTA\n", h[0], h[1], grid, items);
         std::fprintf(stderr, "[gpann stats] clk per item (CTA average): MMA thread total %.0f = wait operands %.0f + wait TMEM slot %.0f + issue %.0f | "

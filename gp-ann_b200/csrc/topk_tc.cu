@@ -286,14 +286,20 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
             if (key >= s.kth[qs]) return false;
             list[s.maxpos[qs]] = key;
         }
+        // new maximum of the list: the keys sit in global memory (L2), so the loads are issued eight at a time instead
+        // of one dependent load per key (a record cost ~3 us of selection-warp time before, ~1M records per sample pass)
         uint64_t m = 0;
         int mp = 0;
-        for (int i = 0; i < s.k; ++i) {
-            const uint64_t x = __ldcg(list + i);
-            if (x >= m) {
-                m = x;
-                mp = i;
-            }
+        for (int i0 = 0; i0 < s.k; i0 += 8) {
+            uint64_t x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (i0 + j < s.k) ? __ldcg(list + i0 + j) : 0ull;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j < s.k && x[j] >= m) {
+                    m = x[j];
+                    mp = i0 + j;
+                }
         }
         s.kth[qs] = m;
         s.maxpos[qs] = mp;
@@ -307,9 +313,12 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
 }
 
 template <bool kFloat>
-__device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel) {
+__device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel,
+                                                 unsigned long long* stats) {
     uint32_t head = 0, idle = 0;
+    unsigned long long n_batches = 0, n_rounds = 0, n_idle = 0, clk_insert = 0, clk_pop = 0;
     while (true) {
+        const long long c_top = stats ? clock64() : 0;
         const uint32_t finished = *done;  // read BEFORE the tail: once all producers are done the tail is final
         __threadfence_block();
         const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(q.tail);
@@ -318,6 +327,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             if (finished == (uint32_t) kEpiWarps) break;
             if ((++idle & 7u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~8 us of idling
             __nanosleep(GPANN_SEL_SLEEP);  // an idle selection warp should cost (almost) no issue slots or power
+            ++n_idle;
             continue;
         }
         const uint32_t n = min(avail, 32u);
@@ -343,8 +353,12 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         __syncwarp();
         head += n;
         if (lane == 0) *q.head = head;  // slots reusable
+        const long long c_ins = stats ? clock64() : 0;
+        clk_pop += (unsigned long long) (c_ins - c_top);
+        ++n_batches;
         // records for the same query are applied one per round (lowest lane first)
         while (__any_sync(0xffffffffu, pending)) {
+            ++n_rounds;
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             bool compact = false;
             if (pending && (__ffs(peers) - 1) == lane) {
@@ -367,6 +381,14 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                 __syncwarp();
             }
         }
+        if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
+    }
+    if (stats && lane == 0 && sel == 0 && blockIdx.x == 0) {  // diagnostics (GPANN_TC_STATS)
+        stats[16] = n_batches;
+        stats[17] = n_rounds;
+        stats[18] = clk_insert;
+        stats[19] = n_idle;
+        stats[20] = clk_pop;
     }
 }
 
@@ -467,6 +489,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    const long long t_kernel0 = stats ? clock64() : 0;
     uint64_t* my_lists = a.cand + (size_t) blockIdx.x * nslots * a.cap;
     const int kb_elems = kFloat ? 64 : 128;  // elements per 128-byte K block
 
@@ -761,6 +784,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         __threadfence_block();
         __syncwarp();
         if (stats && lane == 0) atomicAdd(stats + 1, (unsigned long long) slow_entries);
+        if (stats && lane == 0 && ew == 0 && blockIdx.x == 0) stats[10] = (unsigned long long) (clock64() - t_kernel0);  // filter loop done
         if (stats && lane == 0 && ew == 0) {
             atomicAdd(stats + 5, (unsigned long long) (clock64() - t_begin));
             atomicAdd(stats + 6, (unsigned long long) w_tfull);
@@ -791,13 +815,14 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.eps = a.eps;
         ss.gbound = a.bound ? a.bound + qbase : nullptr;
         ss.nslots = nslots;
-        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel);
+        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
     }
 
     // ---- final selection: every query's k best of this CTA's point range -> partial[s], by all non-role warps ----
     if (warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps + kSelWarps) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + kSelWarps)) : "memory");
+        if (stats && tid == kFilterWarp0 * 32 && blockIdx.x == 0) stats[11] = (unsigned long long) (clock64() - t_kernel0);  // selection warps drained
         for (int qs = warp - kFilterWarp0; qs < nslots; qs += kEpiWarps + kSelWarps) {
             const uint64_t* b = my_lists + (size_t) qs * a.cap;
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
@@ -808,6 +833,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
 
     tcgen05_fence_before();
     __syncthreads();
+    if (stats && tid == 0 && blockIdx.x == 0) stats[12] = (unsigned long long) (clock64() - t_kernel0);  // final selection done
     if (warp == kMmaWarp) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols)
