@@ -351,7 +351,7 @@ struct TcLayout {                 // one norm-sorted tensor layout: a whole poin
 struct TcPlan {
     bool is_float = false;
     int is_signed = 0, d = 0, dp = 0, kblocks = 1, max_r = tc::kMaxR, stages = 3, qcap = 1024;
-    int R = 1, G = 1, k = 0, cap = 128;
+    int R = 1, G = 1, k = 0, cap = 128, lists_smem = 0;
     size_t nqb = 0, nq_pad = 0;
     CUtensorMap tmap_q;
 };
@@ -371,6 +371,14 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
     pl.max_r = pl.kblocks == 1 ? tc::kMaxR : 2;
     pl.stages = pl.kblocks == 1 ? 3 : 2;
     pl.qcap = pl.kblocks == 1 ? 1024 : 512;
+    // small k, one K block: the per-query lists fit in shared memory next to a 2-deep ring (a 3rd stage measured no
+    // faster) and 512-record queues; a candidate record then costs the selection warp ~0.3k clk instead of ~2.8k
+    static const char* e_sl = std::getenv("GPANN_TC_SMEMLISTS");
+    pl.lists_smem = pl.kblocks == 1 && k <= tc::kSmemListKeys && !(e_sl && std::atoi(e_sl) == 0);
+    if (pl.lists_smem) {
+        pl.stages = 2;
+        pl.qcap = 512;
+    }
     // experiment knobs (probes; the defaults above are the tuned plan)
     static const char* e_st = std::getenv("GPANN_TC_STAGES");
     static const char* e_qc = std::getenv("GPANN_TC_QCAP");
@@ -435,6 +443,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.pid = lay.ids;
     a.qnorm = ctx->qnorm.p;
     a.qrows = (const unsigned char*) ctx->qrows.p;
+    a.nq = (int) pl.nqb;
     a.R = pl.R;
     a.G = pl.G;
     a.S = S;
@@ -444,6 +453,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.qcap = pl.qcap;
     a.k = k;
     a.cap = pl.cap;
+    a.lists_smem = pl.lists_smem;
     a.idesc = pl.is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(pl.is_signed);
     a.cand = (uint64_t*) ctx->cand.p;
     a.partial = partial;
@@ -455,7 +465,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.id_base = lay.id_base;
     a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
     const unsigned grid = (unsigned) (pl.G * S);
-    const size_t smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap);
+    const size_t smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
     // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
     // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
     // (a cold start pushes EVERY distance through the selection warps).  Three levels: 1 tile per split (cold, but
@@ -486,8 +496,8 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
                 cudaStreamSynchronize(st);
                 cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
                 std::fprintf(stderr, "[gpann stats] sample pass %u tiles/split: CTA 0 clk: filter loop done %llu, selection drained %llu, final selection done %llu; "
-                                     "records %llu; mma thread clk %llu | CTA 0 selection warp 0: %llu batches, %llu rounds, insert clk %llu, pop clk %llu, idle polls %llu\n",
-                             per_split, h[10], h[11], h[12], h[0], h[2] / grid, h[16], h[17], h[18], h[20], h[19]);
+                                     "records %llu; mma thread clk %llu | CTA 0 selection warp 0: %llu batches, %llu rounds, insert clk %llu, pop clk %llu, idle polls %llu | slowest CTA: set-up %llu, filter loop %llu, whole kernel %llu clk\n",
+                             per_split, h[10], h[11], h[12], h[0], h[2] / grid, h[16], h[17], h[18], h[20], h[19], h[22], h[23], h[21]);
                 a.stats = nullptr;
             }
             TopkOut b;

@@ -105,6 +105,7 @@ constexpr int kFilterWarp0 = GPANN_ROLES_HI ? 0 : 2;  // filter warp w owns TMEM
 constexpr int kSelWarp0 = kFilterWarp0 + kEpiWarps;
 constexpr int kQBlockBytes = kTileM * kRowBytes;  // 16 KB per K block of a query tile
 constexpr int kPBlockBytes = kTileN * kRowBytes;  // 32 KB per K block of a point tile
+constexpr int kSmemListKeys = 16;                // per-query top-k lists live in shared memory when k <= 16 (one K block)
 constexpr uint32_t kPaceWindow = 192;            // tiles a CTA may run ahead of the slowest CTA of its point split
 constexpr int kTmemCols = 512;                   // accumulator slots (+ the resident query tiles when kATmem)
 // Pipeline shape (compile-time, A/B-tested through GPANN_NVCC_EXTRA): an "item" is one MMA accumulator of 128 queries x
@@ -132,11 +133,13 @@ struct Args {
     const uint32_t* pid;     // [n_pad] original ids, kInvalidId on padding rows
     const void* qnorm;       // [G*R*128] squared query norms, same type as pnorm
     const unsigned char* qrows;  // [G*R*128][kblocks*128] prepared query rows (what tmap_q describes); read directly when kATmem
+    int nq;                  // real queries of this batch; slots [nq, G*R*128) are padding
     int R, G, S;             // Q tiles per CTA (1..4), query groups, point splits
     int nks;                 // K steps of 32 bytes (32 byte elements or 16 bf16 elements)
     int kblocks, stages;     // 128-byte K blocks per row; depth of the point-tile ring
     int qcap;                // records per candidate queue (power of two)
     int k, cap;              // top-k and per-query list capacity (power of two >= k + 64)
+    int lists_smem;          // 1: the lists are [R*128][kSmemListKeys] in shared memory (k <= kSmemListKeys), cand unused
     uint32_t tile_lo, tile_stride, ntiles;  // this launch scans tiles tile_lo + i*tile_stride, i in [0,ntiles)
     uint32_t idesc;          // tcgen05 instruction descriptor
     uint64_t* cand;          // [grid, R*128, cap] per-query key lists (global, touched by the selection warps only)
@@ -155,10 +158,11 @@ struct Args {
 };
 
 // Shared-memory footprint (+1 KB so the operand area can be aligned to 1024 bytes).
-inline size_t smem_bytes(int R, int kblocks, int stages, int qcap) {
+inline size_t smem_bytes(int R, int kblocks, int stages, int qcap, int lists_smem) {
     return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
            (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 16 /*queues*/ +
-           (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/;
+           (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/ +
+           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {
     const uint32_t fmt = is_signed ? 1u : 0u;

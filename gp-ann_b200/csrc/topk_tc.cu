@@ -181,8 +181,8 @@ struct SelState {
                        // every CTA (point split) that serves the same queries -- atomicMin when a list tightens, re-read
                        // while the selection warp idles
     int nslots;
-    uint64_t* lists; // global: [nslots][cap] keys of this CTA
-    int k, cap;
+    uint64_t* lists; // [nslots][stride] keys of this CTA: global (L2), or shared memory when k <= kSmemListKeys
+    int k, cap, stride;
     // float path: exact re-rank inputs
     const float* rows_f32;  // [n, d]
     const float* q_f32;     // this CTA's queries [nslots, d]
@@ -275,7 +275,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         const float dist = exact_sqr_l2(s.rows_f32 + (size_t) (id - s.id_base) * s.d, s.q_f32 + (size_t) qs * s.d, s.d);
         key = pack_key(dist, id);
     }
-    uint64_t* list = s.lists + (size_t) qs * s.cap;
+    uint64_t* list = s.lists + (size_t) qs * s.stride;
     int cnt = s.cnt[qs];
     if (s.k <= 32) {
         if (cnt < s.k) {
@@ -293,7 +293,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         for (int i0 = 0; i0 < s.k; i0 += 8) {
             uint64_t x[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (i0 + j < s.k) ? __ldcg(list + i0 + j) : 0ull;
+            for (int j = 0; j < 8; ++j) x[j] = (i0 + j < s.k) ? list[i0 + j] : 0ull;  // generic: the list may be shared memory
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (i0 + j < s.k && x[j] >= m) {
@@ -371,7 +371,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                 const int L = __ffs(need) - 1;
                 need &= need - 1;
                 const uint32_t qsL = __shfl_sync(0xffffffffu, qs, L);
-                uint64_t* b = s.lists + (size_t) qsL * s.cap;
+                uint64_t* b = s.lists + (size_t) qsL * s.stride;
                 const uint64_t newkth = warp_select_topk_dyn<16>(b, s.cap, s.k, b, lane, s.cap);
                 if (lane == L) {
                     s.cnt[qsL] = s.k;
@@ -415,6 +415,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     const int mode = kProbe ? a.mode : 0;
     unsigned long long* const stats = kProbe ? a.stats : nullptr;
+    const long long t_entry = stats ? clock64() : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = a.R, KB = a.kblocks, NST = a.stages;
     const int g = blockIdx.x % a.G, s = blockIdx.x / a.G;
@@ -444,6 +445,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int* s_cnt = s_U + R * kTileM;
     int* s_nq = s_cnt + R * kTileM;                                            // int or float bits
     int* s_maxpos = s_nq + R * kTileM;
+    uint64_t* s_lists = reinterpret_cast<uint64_t*>(s_maxpos + R * kTileM);   // [R*128][kSmemListKeys] when a.lists_smem
 
     const int nslots = R * kTileM;
     const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
@@ -453,14 +455,18 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         s_maxpos[i] = 0;
         // warm start: an upper bound on this query's kth distance from the sample passes (+inf = none)
         const float b = a.bound ? __uint_as_float(a.bound[qbase + i]) : __int_as_float(0x7f800000);
+        // Padding slots (query index >= nq) hold zero vectors: left alone, every low-norm point "beats" their k-th
+        // distance and one CTA per pass drowns in candidate records (measured: the slowest CTA of a sample pass took 35x
+        // the others).  Their threshold is pinned above any accumulator value instead, so they never produce a record.
+        const bool padding = qbase + i >= (size_t) a.nq;
         if (kFloat) {
             const float nqv = reinterpret_cast<const float*>(a.qnorm)[qbase + i];
             s_nq[i] = __float_as_int(nqv);
-            s_U[i] = __float_as_int((b < 3.0e38f) ? nqv - b : -3.0e38f);
+            s_U[i] = __float_as_int(padding ? 3.0e38f : (b < 3.0e38f) ? nqv - b : -3.0e38f);
         } else {
             const int nqv = reinterpret_cast<const int32_t*>(a.qnorm)[qbase + i];
             s_nq[i] = nqv;
-            s_U[i] = (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
+            s_U[i] = padding ? (1 << 29) : (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
         }
     }
     for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qrec[i] = make_uint4(0u, 0u, kQEmpty, 0u);
@@ -490,7 +496,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const long long t_kernel0 = stats ? clock64() : 0;
-    uint64_t* my_lists = a.cand + (size_t) blockIdx.x * nslots * a.cap;
+    if (stats && tid == 0) atomicMax(stats + 22, (unsigned long long) (t_kernel0 - t_entry));  // slowest CTA: set-up phase
+    const int lstride = a.lists_smem ? kSmemListKeys : a.cap;
+    uint64_t* my_lists = a.lists_smem ? s_lists : a.cand + (size_t) blockIdx.x * nslots * a.cap;
     const int kb_elems = kFloat ? 64 : 128;  // elements per 128-byte K block
 
     if (kATmem && warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps) {
@@ -785,6 +793,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         __syncwarp();
         if (stats && lane == 0) atomicAdd(stats + 1, (unsigned long long) slow_entries);
         if (stats && lane == 0 && ew == 0 && blockIdx.x == 0) stats[10] = (unsigned long long) (clock64() - t_kernel0);  // filter loop done
+        if (stats && lane == 0 && ew == 0) atomicMax(stats + 23, (unsigned long long) (clock64() - t_kernel0));  // slowest CTA
         if (stats && lane == 0 && ew == 0) {
             atomicAdd(stats + 5, (unsigned long long) (clock64() - t_begin));
             atomicAdd(stats + 6, (unsigned long long) w_tfull);
@@ -808,6 +817,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.lists = my_lists;
         ss.k = a.k;
         ss.cap = a.cap;
+        ss.stride = lstride;
         ss.rows_f32 = a.rows_f32;
         ss.q_f32 = a.q_f32 ? a.q_f32 + qbase * a.d : nullptr;
         ss.d = a.d;
@@ -824,7 +834,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + kSelWarps)) : "memory");
         if (stats && tid == kFilterWarp0 * 32 && blockIdx.x == 0) stats[11] = (unsigned long long) (clock64() - t_kernel0);  // selection warps drained
         for (int qs = warp - kFilterWarp0; qs < nslots; qs += kEpiWarps + kSelWarps) {
-            const uint64_t* b = my_lists + (size_t) qs * a.cap;
+            const uint64_t* b = my_lists + (size_t) qs * lstride;
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
             const int cnt = s_cnt[qs];
             warp_select_topk_dyn<16>(b, cnt, a.k, dst, lane, min(a.cap, max(32, pow2_ceil(max(cnt, a.k)))));
@@ -838,6 +848,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols)
                      : "memory");
+        if (stats && lane == 0) atomicMax(stats + 21, (unsigned long long) (clock64() - t_entry));  // slowest CTA: whole kernel
     }
 }
 
