@@ -71,7 +71,8 @@ def test_golden_closest_leaders_and_ivf(ctx, gpann_mod):
 @pytest.mark.parametrize("n,d,nq,k,signed", [(20000, 128, 300, 10, False), (5000, 96, 130, 10, False),
                                              (70001, 128, 600, 10, False), (9000, 100, 257, 32, True),
                                              (3000, 128, 128, 100, False), (300, 64, 40, 10, False),
-                                             (255, 128, 17, 1, False)])
+                                             (255, 128, 17, 1, False), (30000, 128, 129, 16, False),
+                                             (30000, 128, 129, 17, False)])
 def test_tensor_bytes_vs_oracle(ctx, gpann_mod, oracle, n, d, nq, k, signed):
     rng = np.random.default_rng(n + d)
     lo, hi = (-128, 128) if signed else (0, 256)
@@ -80,6 +81,20 @@ def test_tensor_bytes_vs_oracle(ctx, gpann_mod, oracle, n, d, nq, k, signed):
     d1, i1, c1, used = _run(ctx, gpann_mod, P, Q, k, gpann_mod.ALGO_TENSOR)
     assert used == ("tensor_s8" if signed else "tensor_u8")
     d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, k)
+    assert_topk_exact(d1, i1, d0, i0, c1, c0)
+
+
+def test_tensor_zero_queries_and_padding_slots(ctx, gpann_mod, oracle):
+    """Real all-zero queries must be answered like any other query, while the zero vectors that pad a batch to a
+    multiple of 128 query slots must stay silent (they are pinned above every accumulator value in the kernel)."""
+    rng = np.random.default_rng(11)
+    P = rng.integers(0, 256, (50000, 128)).astype(np.uint8)
+    P[::997] = 0  # a few zero rows: distance 0 to the zero queries, ties broken by id
+    Q = rng.integers(0, 256, (131, 128)).astype(np.float32)
+    Q[[0, 64, 130]] = 0.0
+    d1, i1, c1, used = _run(ctx, gpann_mod, P, Q, 10, gpann_mod.ALGO_TENSOR)
+    assert used == "tensor_u8"
+    d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, 10)
     assert_topk_exact(d1, i1, d0, i0, c1, c0)
 
 
