@@ -592,7 +592,35 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         uint32_t st = 0, ph = 0, slot = 0, sph = 0;
         long long w_full = 0, w_tempty = 0;
         const long long t_begin = stats ? clock64() : 0;
-        for (uint32_t t = tile_begin; t < tile_end; ++t) {
+        // Full-batch fast path (4 resident query tiles, one K block of 4 steps, two 256-column slots): item 4*tile + r
+        // always lands in slot r & 1 with phase (r >> 1) & 1, so the unrolled loop has constant barrier addresses,
+        // parities and A descriptors -- the issuer's share of the slot hand-shake is a few dozen instructions per item.
+        const bool fast_issue = !kProbe && R == 4 && nks == 4 && KB == 1 && kHalves == 1 && kSlots == 2;
+        for (uint32_t t = tile_begin; fast_issue && t < tile_end; ++t) {
+            mbar_wait(bar_full + 8 * st, ph);
+            tcgen05_fence_after();
+            const uint64_t b_st = b_base + ((st * p_tile_bytes) >> 4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                mbar_wait(bar_tempty + 8 * (r & 1), ((r >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t dcol = tmem_base + (r & 1) * kAccN;
+                    const uint64_t a_r = a_base + (uint32_t) (r * (kQBlockBytes >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) issue_mma<kFloat>(dcol, a_r + 2 * ks, b_st + 2 * ks, r * 32 + 8 * ks, tmem_base, idesc, ks > 0);
+                    umma_commit(bar_tfull + 8 * (r & 1));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar_empty + 8 * st);
+            __syncwarp();
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        for (uint32_t t = tile_begin; !fast_issue && t < tile_end; ++t) {
             const long long c0 = stats ? clock64() : 0;
             mbar_wait(bar_full + 8 * st, ph);
             if (stats) w_full += clock64() - c0;
