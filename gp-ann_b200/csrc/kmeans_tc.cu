@@ -195,45 +195,61 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // ===== TMA producer: this split's centroids once, then the point tiles =====
             mbar_expect_tx(bar_b, (uint32_t) NKB2 * b_block_bytes);
             for (int kb = 0; kb < NKB2; ++kb) tma_load_2d(sB + kb * b_block_bytes, &tmap_b, bar_b, kb * kKBlockElems, cs * NB);
-            uint32_t tl = 0;
-            for (uint32_t t = pg; t < a.ntiles; t += PG, ++tl) {
-                const uint32_t st = tl % NST, ph = (tl / NST) & 1;
+            uint32_t st = 0, ph = 0;
+            for (uint32_t t = pg; t < a.ntiles; t += PG) {
                 mbar_wait(bar_empty + 8 * st, ph ^ 1);
                 mbar_expect_tx(bar_full + 8 * st, a_tile_bytes);
                 for (int kb = 0; kb < NKB2; ++kb)
                     tma_load_2d(sA + st * a_tile_bytes + kb * kABlockBytes, &tmap_a, bar_full + 8 * st, kb * kKBlockElems,
                                 (int) (t * kTileM));
+                if (++st == (uint32_t) NST) {
+                    st = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer: acc = xh.cl + xl.ch + xh.ch (small terms first) =====
-            mbar_wait(bar_b, 0);
+        // ===== MMA issuer: acc = xh.cl + xl.ch + xh.ch (small terms first).  The whole warp walks the loop and one
+        // elected lane issues a tile's MMAs + commits (see topk_tc.cu: a lane-0-only loop costs an ELECT/branch wrapper
+        // and fresh descriptor arithmetic per tcgen05.mma and ends up issue-bound); descriptors are base + constant.
+        mbar_wait(bar_b, 0);
+        tcgen05_fence_after();
+        const uint64_t a_base = make_sw64_desc(sA), b_base = make_sw64_desc(sB);
+        const uint32_t idesc = a.idesc;
+        const int nks = a.nks, nkb = a.nkb;
+        uint32_t st = 0, ph = 0, slot = 0, sph = 0;
+        for (uint32_t t = pg; t < a.ntiles; t += PG) {
+            mbar_wait(bar_full + 8 * st, ph);
+            mbar_wait(bar_tempty + 8 * slot, sph ^ 1);
             tcgen05_fence_after();
-            uint32_t tl = 0;
-            for (uint32_t t = pg; t < a.ntiles; t += PG, ++tl) {
-                const uint32_t st = tl % NST, ph = (tl / NST) & 1;
-                const uint32_t slot = tl & 1, sph = (tl >> 1) & 1;
-                mbar_wait(bar_full + 8 * st, ph);
-                mbar_wait(bar_tempty + 8 * slot, sph ^ 1);
-                tcgen05_fence_after();
+            if (elect_one()) {
                 const uint32_t dcol = tmem_base + slot * NB;
+                const uint64_t a_st = a_base + ((st * a_tile_bytes) >> 4);
                 uint32_t acc = 0;
-#pragma unroll 1
+#pragma unroll
                 for (int term = 0; term < 3; ++term) {
                     const int ta = term == 1 ? 1 : 0;  // A part: hi, lo, hi
                     const int tb = term == 0 ? 1 : 0;  // B part: lo, hi, hi
-                    for (int ks = 0; ks < a.nks; ++ks) {
+                    const uint64_t a_t = a_st + (uint32_t) ((ta * nkb * kABlockBytes) >> 4);
+                    const uint64_t b_t = b_base + (uint32_t) ((tb * nkb * (int) b_block_bytes) >> 4);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        // K step ks = 16 bf16 = 32 bytes: block ks/2 of the part, +2 (16-byte units) for the second half
                         const int kb = ks >> 1, w = ks & 1;
-                        const uint64_t adesc = make_sw64_desc(sA + st * a_tile_bytes + (ta * a.nkb + kb) * kABlockBytes) + 2 * w;
-                        const uint64_t bdesc = make_sw64_desc(sB + (tb * a.nkb + kb) * b_block_bytes) + 2 * w;
-                        umma_bf16(dcol, adesc, bdesc, a.idesc, acc);
+                        umma_bf16(dcol, a_t + (uint32_t) (kb * (kABlockBytes >> 4) + 2 * w), b_t + (uint32_t) (kb * (int) (b_block_bytes >> 4) + 2 * w),
+                                  idesc, acc);
                         acc = 1;
                     }
                 }
                 umma_commit(bar_tfull + 8 * slot);
                 umma_commit(bar_empty + 8 * st);
             }
+            __syncwarp();
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
+            slot ^= 1;
+            sph ^= (slot == 0);
         }
     } else {
         // ===== filter warps =====

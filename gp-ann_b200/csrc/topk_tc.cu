@@ -481,7 +481,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         mbar_init(bar_q, kATmem ? kEpiWarps : 1);
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, kEpiWarps);  // one arrive per filter warp
+            mbar_init(bar_tempty + 8 * i, kFilterByItem ? kEpiWarps / 2 : kEpiWarps);  // one arrive per filter warp on the item
         }
         fence_barrier_init();
     }
@@ -683,9 +683,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const int wq = warp & 3;
         const int qrow = wq * 32 + lane;
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
-        constexpr int kColsPerWarp = kAccN / (kEpiWarps / 4);
+        // kFilterByItem: the two groups of four filter warps take alternate items (group = accumulator slot) and drain all
+        // kAccN columns of their lane quadrant; otherwise every warp drains its column group of every item.
+        constexpr int kColsPerWarp = kFilterByItem ? kAccN : kAccN / (kEpiWarps / 4);
         static_assert(kColsPerWarp % 64 == 0, "a filter warp drains 64 columns at a time");
-        const int col_base = half * kColsPerWarp;  // this warp's columns inside an accumulator
+        const int col_base = kFilterByItem ? 0 : half * kColsPerWarp;  // this warp's columns inside an accumulator
         uint32_t slow_entries = 0;
         // the selection warp that owns this warp's queries: (qs >> 5) & 1 = (4 r + wq) & 1 = wq & 1 for every r
         const int sel = wq & (kSelWarps - 1);
@@ -720,16 +722,18 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             }
             for (int r = 0; r < R; ++r) {
                 const uint32_t qs = (uint32_t) (r * kTileM + qrow);
-                const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
-                const int nqraw = s_nq[qs];
 #pragma unroll
                 for (int h = 0; h < kHalves; ++h) {
                     const uint32_t bar_tf = bar_tfull + 8 * slot, bar_te = bar_tempty + 8 * slot, par_tf = sph;
                     const uint32_t tbase = tbase0 + slot * kAccN;
+                    const bool mine = !kFilterByItem || slot == (uint32_t) half;
                     if (++slot == (uint32_t) kSlots) {
                         slot = 0;
                         sph ^= 1;
                     }
+                    if (!mine) continue;
+                    const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
+                    const int nqraw = s_nq[qs];
                     const int row0 = h * kAccN;  // first tile row of this item
                     int Ti = 0;
                     float Tf = 0.f;
