@@ -390,41 +390,83 @@ __global__ void kmeans_finalize_kernel(const KmFinalizeParams p) {
 // Squared L2 distance of two global fp32 rows in the reference's summation order (src/dist.cpp:9-16 -> hnswlib
 // space_l2.h:60-91, 6-20).
 __device__ __forceinline__ float exact_l2(const float* __restrict__ x, const float* __restrict__ q, int d) {
+    if ((d & 3) == 0 && (((uintptr_t) x | (uintptr_t) q) & 15) == 0) {
+        // same arithmetic, 16-byte loads: lane l of the reference's 8 accumulators takes elements i = l (mod 8)
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f, l5 = 0.f, l6 = 0.f, l7 = 0.f;
+        const int d16 = d & ~15;
+        for (int i = 0; i < d16; i += 8) {
+            const float4 xa = __ldg(reinterpret_cast<const float4*>(x + i)), xb = __ldg(reinterpret_cast<const float4*>(x + i + 4));
+            const float4 qa = __ldg(reinterpret_cast<const float4*>(q + i)), qb = __ldg(reinterpret_cast<const float4*>(q + i + 4));
+            float t;
+            t = xa.x - qa.x; l0 = __fmaf_rn(t, t, l0);
+            t = xa.y - qa.y; l1 = __fmaf_rn(t, t, l1);
+            t = xa.z - qa.z; l2 = __fmaf_rn(t, t, l2);
+            t = xa.w - qa.w; l3 = __fmaf_rn(t, t, l3);
+            t = xb.x - qb.x; l4 = __fmaf_rn(t, t, l4);
+            t = xb.y - qb.y; l5 = __fmaf_rn(t, t, l5);
+            t = xb.z - qb.z; l6 = __fmaf_rn(t, t, l6);
+            t = xb.w - qb.w; l7 = __fmaf_rn(t, t, l7);
+        }
+        const float res = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(l0, l1), l2), l3), l4), l5), l6), l7);
+        float tail = 0.f;
+        for (int i = d16; i < d; ++i) {
+            const float t = x[i] - q[i];
+            tail = __fmaf_rn(t, t, tail);
+        }
+        return __fadd_rn(res, tail);
+    }
     return sqr_l2_ref_order([x](int i) { return x[i]; }, q, d);
 }
 
-// One warp per ambiguous point: exact distances to its candidate centroids (a pair, one 32-centroid chunk (+ the runner
-// up), or all of them), minimum (distance, index) key = the reference's strict-< scan (src/kmeans.cpp:16-21).
+// Exact re-rank of the ambiguous points: distances to the candidate centroids (a pair, one 32-centroid chunk, or all of
+// them), minimum (distance, index) key = the reference's strict-< scan (src/kmeans.cpp:16-21).  A warp takes 16 list
+// entries at a time: the common case, a pair of candidates, is settled by the entry's own two lanes (16 points per warp
+// pass instead of one); chunk / full entries are then re-ranked by the whole warp, one after the other.
 __global__ void kmeans_resolve_kernel(const KmFinalizeParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t total = *p.amb_count;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
-        const uint32_t i = p.amb_list[w];
-        const uint2 raw = p.amb_info[w];
-        const uint3 info = make_uint3(raw.x, raw.y & 0x3FFFFFFFu, raw.y >> 30);
-        const float* x = p.rows + (size_t) i * p.d;
+    const uint32_t groups = (total + 15u) / 16u;
+    for (uint32_t gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gidx < groups; gidx += warps) {
+        const uint32_t w = gidx * 16u + (uint32_t) (lane >> 1);
+        const bool valid = w < total;
+        const uint32_t i = valid ? p.amb_list[w] : 0u;
+        const uint2 raw = valid ? p.amb_info[w] : make_uint2(0u, 0u);
+        const uint32_t mode = raw.y >> 30;
         uint64_t best = kEmptyKey;
-        if (info.z == kModePair) {
-            if (lane < 2) {
-                const int j = lane == 0 ? (int) info.x : (int) info.y;
-                best = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
-            }
-        } else if (info.z == kModeChunk) {
-            const int j = (int) (info.x & ~31u) + lane;
-            if (j < p.kc) best = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
-        } else {
-            for (int j = lane; j < p.kc; j += 32) {
-                const uint64_t key = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
-                best = key < best ? key : best;
-            }
+        if (valid && mode == kModePair) {
+            const int j = (lane & 1) == 0 ? (int) raw.x : (int) (raw.y & 0x3FFFFFFFu);
+            best = pack_key(exact_l2(p.rows + (size_t) i * p.d, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
         }
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, best, 1);
+        best = other < best ? other : best;
+        if (valid && mode == kModePair && (lane & 1) == 0) p.out_assign[i] = key_dist(best) < 3.402823466e+38f ? (int32_t) key_id(best) : -1;
+        // entries that need more than a pair: one at a time, warp-wide
+        unsigned pending = __ballot_sync(0xffffffffu, valid && mode != kModePair && (lane & 1) == 0);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t pi = __shfl_sync(0xffffffffu, i, src);
+            const uint32_t px = __shfl_sync(0xffffffffu, raw.x, src);
+            const uint32_t pm = __shfl_sync(0xffffffffu, mode, src);
+            const float* x = p.rows + (size_t) pi * p.d;
+            uint64_t b = kEmptyKey;
+            if (pm == kModeChunk) {
+                const int j = (int) (px & ~31u) + lane;
+                if (j < p.kc) b = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
+            } else {
+                for (int j = lane; j < p.kc; j += 32) {
+                    const uint64_t key = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
+                    b = key < b ? key : b;
+                }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other < best ? other : best;
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ob = __shfl_xor_sync(0xffffffffu, b, o);
+                b = ob < b ? ob : b;
+            }
+            if (lane == 0) p.out_assign[pi] = key_dist(b) < 3.402823466e+38f ? (int32_t) key_id(b) : -1;
         }
-        if (lane == 0) p.out_assign[i] = key_dist(best) < 3.402823466e+38f ? (int32_t) key_id(best) : -1;
     }
 }
 
