@@ -511,7 +511,9 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.ntiles = tiles_total;
     a.sample_pass = 0;
     static const bool no_pace = std::getenv("GPANN_TC_NOPACE") != nullptr;
-    if (!no_pace && tiles_total / S >= 4 * tc::kPaceWindow && pl.G > 1 && (int) grid <= ctx->num_sms) {  // all CTAs co-resident
+    const char* e_pw = std::getenv("GPANN_TC_PACE_WINDOW");  // tests: a tight window exercises the pacing protocol on small sets
+    a.pace_window = e_pw ? (uint32_t) std::max(1, std::atoi(e_pw)) : tc::kPaceWindow;
+    if (!no_pace && tiles_total / S >= 4 * a.pace_window && pl.G > 1 && (int) grid <= ctx->num_sms) {  // all CTAs co-resident
         GP_TRY(reserve(ctx, ctx->pace, (size_t) grid * sizeof(uint32_t)));
         CU_TRY(ctx, cudaMemsetAsync(ctx->pace.p, 0, (size_t) grid * sizeof(uint32_t), st));
         a.pace = (uint32_t*) ctx->pace.p;

@@ -158,6 +158,7 @@ struct Args {
     uint32_t id_base;
     float eps;               // relative error bound of the bf16 dot product: |dot~ - dot| <= eps*|q|*|x|
     int sample_pass;         // 1 for the strided pre-passes: their only product is an upper bound per query
+    uint32_t pace_window;    // tiles a CTA may run ahead of the slowest CTA of its split (kPaceWindow; tests shrink it)
     uint32_t* pace;          // optional [S*G] tile positions of the CTAs (zeroed before the launch): L2 pacing of a split's CTAs
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
 };

@@ -546,12 +546,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 if (pace && ((t - tile_begin) & 31u) == 0) {
                     const uint32_t tl = t - tile_begin;
                     pace[g] = tl;
-                    if (tl >= kPaceWindow) {
+                    if (tl >= a.pace_window) {
                         const uint64_t t0 = global_timer_ns();
                         for (;;) {
                             uint32_t slowest = 0xFFFFFFFFu;
                             for (int j = 0; j < a.G; ++j) slowest = min(slowest, pace[j]);
-                            if (slowest + kPaceWindow >= tl) break;
+                            if (slowest + a.pace_window >= tl) break;
                             __nanosleep(2000);
                             if (global_timer_ns() - t0 > 5000000ull) {  // a peer is not running (not co-resident?): stop pacing
                                 pace = nullptr;

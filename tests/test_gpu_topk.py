@@ -98,6 +98,20 @@ def test_tensor_zero_queries_and_padding_slots(ctx, gpann_mod, oracle):
     assert_topk_exact(d1, i1, d0, i0, c1, c0)
 
 
+def test_tensor_paced_splits_bit_exact(ctx, gpann_mod, oracle, monkeypatch):
+    """The CTAs of a point split pace each other inside an L2 window (topk_tc.cu, TMA producer).  With a window of 8
+    tiles the protocol (publish, wait for the slowest, finished CTAs release the others) runs constantly on a set small
+    enough for the oracle; several query groups (nq > 512) are needed for a split to have more than one CTA."""
+    monkeypatch.setenv("GPANN_TC_PACE_WINDOW", "8")
+    rng = np.random.default_rng(21)
+    P = rng.integers(0, 256, (1_500_000, 128)).astype(np.uint8)
+    Q = rng.integers(0, 256, (700, 128)).astype(np.float32)
+    d1, i1, c1, used = _run(ctx, gpann_mod, P, Q, 10, gpann_mod.ALGO_TENSOR)
+    assert used == "tensor_u8"
+    d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, 10)
+    assert_topk_exact(d1, i1, d0, i0, c1, c0)
+
+
 def test_tensor_heavy_ties_and_duplicates(ctx, gpann_mod, oracle):
     rng = np.random.default_rng(5)
     P = rng.integers(0, 2, (4000, 128)).astype(np.uint8)
