@@ -162,7 +162,10 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                    bar_tfull = bar_b + 8, bar_tempty = bar_tfull + 16;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(after + 8 * (2 * kMaxStages + 5));
     float* s_hn = reinterpret_cast<float*>(after + 256);             // [NB]
-    uint4* s_part = reinterpret_cast<uint4*>(s_hn + NB);             // [2][128]
+    uint4* s_part = reinterpret_cast<uint4*>(s_hn + NB);             // [2][kFilterWarps/4 - 1][128]
+    // column groups of 64 (or more) columns: NB = 256 with 16 filter warps -> 4 groups; warps beyond the last group idle
+    constexpr int kMaxGroups = kFilterWarps / 4;
+    const int ngroups = min(kMaxGroups, NB / 64);
 
     for (int i = tid; i < NB; i += kThreads) s_hn[i] = a.hnp[(size_t) cs * NB + i];
     if (warp == 0 && lane == 0) {
@@ -175,7 +178,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_init(bar_b, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, kFilterWarps);
+            mbar_init(bar_tempty + 8 * i, 4 * ngroups);  // one arrive per working filter warp
         }
         fence_barrier_init();
     }
@@ -254,15 +257,15 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else {
         // ===== filter warps =====
         const int ew = warp - 2;
-        const int half = ew >> 2;
+        const int grp = ew >> 2;              // column group of this warp
         const int wq = warp & 3;
         const int qrow = wq * 32 + lane;
         const uint32_t lane_sel = (uint32_t) (wq * 32) << 16;
-        const int ncol = NB >> 1;             // columns of this warp: [half*ncol, +ncol)
-        const int col_base = half * ncol;
+        const int ncol = NB / ngroups;        // columns of this warp: [grp*ncol, +ncol)
+        const int col_base = grp * ncol;
         const uint32_t cid_base = (uint32_t) (col_base >> 5);
         uint32_t tl = 0;
-        for (uint32_t t = pg; t < a.ntiles; t += PG, ++tl) {
+        for (uint32_t t = pg; grp < ngroups && t < a.ntiles; t += PG, ++tl) {
             const uint32_t slot = tl & 1, sph = (tl >> 1) & 1;
             Top3 top;
             top.e1 = top.e2 = top.e3 = -1;
@@ -297,15 +300,17 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 top3_insert(top, c1, cid);
                 top3_insert(top, c2, cid);
             }
-            // merge the two column halves of a point through shared memory; half 0 writes the result
-            uint4* part = s_part + (tl & 1) * kTileM;
-            if (half == 1) part[qrow] = make_uint4((uint32_t) top.e1, (uint32_t) top.e2, (uint32_t) top.e3, top.ids);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
-            if (half == 0) {
-                const uint4 o = part[qrow];
-                top3_insert(top, (int) o.x, o.w & 0xFu);
-                top3_insert(top, (int) o.y, (o.w >> 4) & 0xFu);
-                top3_insert(top, (int) o.z, (o.w >> 8) & 0xFu);
+            // merge the column groups of a point through shared memory; group 0 writes the result
+            uint4* part = s_part + (size_t) (tl & 1) * (kMaxGroups - 1) * kTileM;
+            if (grp > 0) part[(grp - 1) * kTileM + qrow] = make_uint4((uint32_t) top.e1, (uint32_t) top.e2, (uint32_t) top.e3, top.ids);
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + wq), "r"(32 * ngroups) : "memory");
+            if (grp == 0) {
+                for (int og = 1; og < ngroups; ++og) {
+                    const uint4 o = part[(og - 1) * kTileM + qrow];
+                    top3_insert(top, (int) o.x, o.w & 0xFu);
+                    top3_insert(top, (int) o.y, (o.w >> 4) & 0xFu);
+                    top3_insert(top, (int) o.z, (o.w >> 8) & 0xFu);
+                }
                 a.partial[(size_t) cs * ((size_t) a.ntiles * kTileM) + (size_t) t * kTileM + qrow] =
                     make_uint4((uint32_t) top.e1, (uint32_t) top.e2, (uint32_t) top.e3, top.ids);
             }

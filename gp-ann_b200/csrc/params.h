@@ -188,7 +188,11 @@ namespace kmtc {
 constexpr int kTileM = 128;       // points per tile (UMMA M, TMEM lanes)
 constexpr int kKBlockElems = 32;  // bf16 elements per K block = one SWIZZLE_64B row (64 bytes)
 constexpr int kMaxStages = 3;
-constexpr int kFilterWarps = 8;   // 4 TMEM lane quadrants x 2 column halves
+#ifndef GPANN_KM_FILTER_WARPS
+#define GPANN_KM_FILTER_WARPS 16
+#endif
+constexpr int kFilterWarps = GPANN_KM_FILTER_WARPS;  // 4 TMEM lane quadrants x (kFilterWarps/4) column groups; the epilogue is
+                                                     // ALU-bound (~130 instructions per 32 scores), so 4 warps per sub-partition
 constexpr int kThreads = 64 + 32 * kFilterWarps;
 constexpr int kABlockBytes = kTileM * 64;  // 8 KB per K block of a point tile
 
@@ -215,7 +219,7 @@ struct Args {
 
 inline size_t smem_bytes(int NB, int nkb, int stages) {
     return 1024 + (size_t) 2 * nkb * NB * 64 /*centroids*/ + (size_t) stages * 2 * nkb * kABlockBytes /*point tiles*/ +
-           256 /*barriers*/ + (size_t) NB * 4 /*hn'*/ + (size_t) 2 * kTileM * 16 /*half-merge buffers*/;
+           256 /*barriers*/ + (size_t) NB * 4 /*hn'*/ + (size_t) 2 * (kFilterWarps / 4 - 1) * kTileM * 16 /*group-merge buffers*/;
 }
 inline uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (kTileM >> 4) << 24);
