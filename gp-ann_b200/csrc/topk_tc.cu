@@ -42,6 +42,10 @@
 #ifndef GPANN_SPIN
 #define GPANN_SPIN 0
 #endif
+// 1: a filter warp loads all of its columns of an item before it releases the accumulator slot (128 data registers)
+#ifndef GPANN_DRAIN_ALL
+#define GPANN_DRAIN_ALL 0
+#endif
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
 #endif
@@ -774,16 +778,28 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                     // of single x32 loads (next chunk in flight during the max tree) was measured SLOWER (120 -> 135 ms):
                     // the TMEM read path is not the limit (~1 KB/clk/SM, profiles/tools/tmem_ld_bench.cu); what matters is
                     // how soon after tcgen05.commit the slot goes back to the MMA issuer.
+                    uint32_t vv[kColsPerWarp / 32][32];
+                    if (GPANN_DRAIN_ALL) {  // variant: every column of the warp into registers first, slot back at once
+#pragma unroll
+                        for (int j = 0; j < kColsPerWarp / 32; ++j) tmem_ld32(tbase + j * 32, vv[j]);
+                        tmem_wait_ld();
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_te);
+                    }
 #pragma unroll
                     for (int c = 0; c < kColsPerWarp / 64; ++c) {
-                        uint32_t va[32], vb[32];
-                        tmem_ld32(tbase + c * 64, va);
-                        tmem_ld32(tbase + c * 64 + 32, vb);
-                        tmem_wait_ld();
-                        if (c == kColsPerWarp / 64 - 1) {  // accumulator drained into registers: hand the slot back before the
-                            tcgen05_fence_before();        // arithmetic, so a slow-path entry on this half cannot stall the MMA
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_te);
+                        uint32_t (&va)[32] = vv[2 * c];
+                        uint32_t (&vb)[32] = vv[2 * c + 1];
+                        if (!GPANN_DRAIN_ALL) {
+                            tmem_ld32(tbase + c * 64, va);
+                            tmem_ld32(tbase + c * 64 + 32, vb);
+                            tmem_wait_ld();
+                            if (c == kColsPerWarp / 64 - 1) {  // accumulator drained into registers: hand the slot back before
+                                tcgen05_fence_before();        // the arithmetic, so a slow-path entry cannot stall the MMA
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar_te);
+                            }
                         }
                         const int col0 = row0 + col_base + c * 64;  // tile row of va[0]
                         if (kFloat) {
