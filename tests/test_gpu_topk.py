@@ -72,7 +72,8 @@ def test_golden_closest_leaders_and_ivf(ctx, gpann_mod):
                                              (70001, 128, 600, 10, False), (9000, 100, 257, 32, True),
                                              (3000, 128, 128, 100, False), (300, 64, 40, 10, False),
                                              (255, 128, 17, 1, False), (30000, 128, 129, 16, False),
-                                             (30000, 128, 129, 17, False)])
+                                             (30000, 128, 129, 17, False), (40000, 96, 700, 10, False),
+                                             (40000, 128, 700, 10, True)])
 def test_tensor_bytes_vs_oracle(ctx, gpann_mod, oracle, n, d, nq, k, signed):
     rng = np.random.default_rng(n + d)
     lo, hi = (-128, 128) if signed else (0, 256)
@@ -257,7 +258,7 @@ def test_sharded_topk_device_path_matches_single_scan(ctx, gpann_mod, oracle):
 @pytest.mark.parametrize("n,d,nq,k,kind", [(20000, 128, 300, 10, "normal"), (30000, 96, 130, 100, "normal"),
                                            (50001, 100, 257, 10, "normal"), (8000, 64, 40, 10, "normal"),
                                            (20000, 128, 100, 10, "offset"), (20000, 96, 100, 10, "unit"),
-                                           (6000, 20, 50, 5, "clustered")])
+                                           (6000, 20, 50, 5, "clustered"), (20000, 64, 600, 10, "normal")])
 def test_tensor_float_vs_oracle(ctx, gpann_mod, oracle, n, d, nq, k, kind):
     rng = np.random.default_rng(n + d + k)
     P = rng.standard_normal((n, d)).astype(np.float32)
