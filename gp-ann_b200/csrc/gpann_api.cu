@@ -472,7 +472,10 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     // tiny), then 12 and 160 tiles per split, each filtered by the previous level's bound.  (During a pass the CTAs of
     // different point splits also share their k-th distances through a.bound, see publish_threshold.)
     if (prepass && ctx->tc_prepass && ctx->tc_mode == 0 && !(ctx->tc_warm && ctx->tc_warm_valid)) {
-        uint32_t levels[3] = { 1, 12, 160 };
+        // level sizes follow the shard: a third level of 160 tiles per split is 8 % of a 12.5M-row shard's work
+        const uint32_t per_split_tiles = tiles_total / (uint32_t) S;
+        const uint32_t l3 = std::max(16u, std::min(160u, per_split_tiles / 96u));
+        uint32_t levels[3] = { 1, std::max(4u, std::min(12u, l3 / 12u)), l3 };
         static const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment knob: "a/b/c" tiles per split (0 = skip the level)
         if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
         for (uint32_t per_split : levels) {
