@@ -474,8 +474,9 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     if (prepass && ctx->tc_prepass && ctx->tc_mode == 0 && !(ctx->tc_warm && ctx->tc_warm_valid)) {
         // level sizes follow the shard: a third level of 160 tiles per split is 8 % of a 12.5M-row shard's work
         const uint32_t per_split_tiles = tiles_total / (uint32_t) S;
-        const uint32_t l3 = std::max(16u, std::min(160u, per_split_tiles / 96u));
-        uint32_t levels[3] = { 1, std::max(4u, std::min(12u, l3 / 12u)), l3 };
+        uint32_t l3 = std::min(160u, per_split_tiles / 96u);
+        if (l3 < 24u) l3 = 0;  // small splits: two levels (measured: a third costs more than it saves at 1M points)
+        uint32_t levels[3] = { 1, l3 ? std::max(4u, std::min(12u, l3 / 12u)) : 12u, l3 };
         static const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment knob: "a/b/c" tiles per split (0 = skip the level)
         if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
         for (uint32_t per_split : levels) {
