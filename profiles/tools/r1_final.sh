@@ -2,6 +2,11 @@
 # Round-1 evidence run on ONE B200 (under gpurun): GPU test suite, bench.py (own arm + reference arm), launch list, one
 # ncu --set full capture of the dominant kernel, microbenchmarks, and the other configs.  Outputs -> gpurun_out/.
 OUT=gpurun_out; mkdir -p $OUT
+# microbenchmarks (not part of the library): build on first use
+mkdir -p profiles/tools/_bin
+for b in mma_issue_bench tmem_ld_bench; do
+  [ -x profiles/tools/_bin/$b ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/tools/_bin/$b profiles/tools/$b.cu 2>/dev/null
+done
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/final_gpu.txt 2>&1
 echo "#### pytest -m gpu" > $OUT/final_tests.txt
 timeout 900 python -m pytest tests -m gpu -x -q >> $OUT/final_tests.txt 2>&1
