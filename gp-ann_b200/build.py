@@ -16,8 +16,8 @@ TAG = os.environ.get("GPANN_BUILD_TAG", "")
 EXTRA = os.environ.get("GPANN_NVCC_EXTRA", "").split()
 OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 OUT = os.path.join(HERE, "libgpann_cuda" + ("_" + TAG if TAG else "") + ".so")
-SOURCES = ["gpann_api.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
-HEADERS = ["common.cuh", "distance.cuh", "params.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "gpann.h")]
+SOURCES = ["gpann_api.cu", "abi.cu", "multi.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
+HEADERS = ["common.cuh", "distance.cuh", "params.h", "tc_ptx.cuh", "api_internal.h", os.path.join("..", "..", "include", "gpann.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 
@@ -53,22 +53,46 @@ def build(force=False, verbose=False):
         results = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
     objs = [o for o, _ in results]
     if force or any(changed for _, changed in results) or not os.path.exists(OUT):
-        subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
+        subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-ldl", "-lpthread"])
     if not TAG:
         build_dropin(force)
     return OUT
 
 
 def build_dropin(force=False):
-    """libgpann_dropin.so: the C++ drop-in layer (cxx/: reference-shaped dist.h/topn.h/recall.h/kmeans.h over the C
-    ABI) behind a small C shim, so the tests can drive it.  Plain g++, links libgpann_cuda.so via $ORIGIN."""
+    """libgpann_dropin.so: the C++ drop-in layer (cxx/: recall.h, kmeans_gpu.cpp over the C ABI; cxx/standalone/: the
+    reference-shaped defs.h/topn.h/dist.h/kmeans.h for builds without a gp-ann checkout) behind a small C shim, so the
+    tests can drive it.  Plain g++, links libgpann_cuda.so via $ORIGIN."""
     cxx = os.path.join(HERE, "cxx")
+    sa = os.path.join(cxx, "standalone")
     out = os.path.join(HERE, "libgpann_dropin.so")
-    srcs = [os.path.join(cxx, f) for f in ("dropin_shim.cpp", "dist.cpp", "kmeans_gpu.cpp")]
+    srcs = [os.path.join(cxx, "dropin_shim.cpp"), os.path.join(cxx, "kmeans_gpu.cpp"), os.path.join(sa, "dist.cpp"),
+            os.path.join(sa, "defs.cpp")]
+    deps = srcs + [os.path.join(cxx, f) for f in os.listdir(cxx)] + [os.path.join(sa, f) for f in os.listdir(sa)] + [OUT]
+    if force or _stale(out, deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-I" + cxx, "-I" + sa, "-o", out, *srcs,
+                               "-L" + HERE, "-lgpann_cuda", "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
+def build_integration(ref="/root/reference", force=False):
+    """tests/_build/libgpann_integration.so: INTEGRATION.md's recipe executed -- the reference's UNMODIFIED
+    kmeans_tree_router.cpp / defs.cpp / dist.cpp and its own headers (defs.h, topn.h, dist.h, kmeans.h), with
+    `-I cxx` ahead of `-I <gp-ann>/src` so that recall.h is the drop-in's, plus cxx/kmeans_gpu.cpp and libgpann_cuda.so.
+    Needs the reference checkout (absent on the GPU box: the prebuilt .so travels).  Returns the path or None."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tests", "_build", "libgpann_integration.so")
+    if not os.path.exists(os.path.join(ref, "src", "kmeans_tree_router.cpp")):
+        return out if os.path.exists(out) else None
+    cxx = os.path.join(HERE, "cxx")
+    srcs = [os.path.join(root, "tests", "integration", "router_shim.cpp"), os.path.join(cxx, "kmeans_gpu.cpp"),
+            os.path.join(ref, "src", "kmeans_tree_router.cpp"), os.path.join(ref, "src", "defs.cpp"), os.path.join(ref, "src", "dist.cpp")]
     deps = srcs + [os.path.join(cxx, f) for f in os.listdir(cxx)] + [OUT]
     if force or _stale(out, deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-o", out, *srcs,
-                               "-L" + HERE, "-lgpann_cuda", "-Wl,-rpath,$ORIGIN"])
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-pthread", "-w",
+                               "-I" + cxx, "-I" + os.path.join(ref, "src"), "-I" + os.path.join(ref, "external", "parlaylib", "include"),
+                               "-o", out, *srcs, "-L" + HERE, "-lgpann_cuda", "-Wl,-rpath," + HERE + ":$ORIGIN/../../gp-ann_b200"])
     return out
 
 

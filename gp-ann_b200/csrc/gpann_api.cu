@@ -12,138 +12,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/gpann.h"
-#include "common.cuh"
-#include "params.h"
+#include "api_internal.h"
 
 using namespace gpann;
 
-// ---- handles ---------------------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-struct gpann_ctx {
-    int device = 0;
-    int num_sms = 0;
-    int algo = GPANN_ALGO_AUTO;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    uint64_t launches = 0;
-    const char* last_algo = "none";
-    EncodeTiledFn encode_tiled = nullptr;
-    int tc_mode = 0;     // GPANN_TC_MODE env: 1 = probe (MMA + TMEM loads + max), 2 = probe (MMA issue only)
-    int tc_prepass = 1;  // GPANN_TC_PREPASS env: 0 disables the sample pre-pass (cold-start thresholds)
-    int tc_warm = 0;     // GPANN_TC_WARM env (probe): keep the previous call's k-th distances as the next call's bounds
-    bool tc_warm_valid = false;
-    int timing = 0;
-    bool timed = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // grow-only scratch, reused across calls (a ctx is externally synchronised)
-    DevBuf pace;
-    DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
-        sort_d, segsums, cent, sums, counts, assign, km_cent, km_hn, km_scal, km_partial, km_amb_list, km_amb_info;
-    int km_mode = 0;     // GPANN_KM_MODE env: 2 = probe (MMA issue only, results invalid)
-    // streaming entry points: second stream for the H2D copies, double-buffered raw chunks, one chunk layout
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
-    DevBuf st_raw[2], st_rows, st_norms, st_ids, st_a, st_b, st_c, st_d, st_tmp, st_narrow;
-};
-
-struct gpann_points {
-    gpann_ctx* ctx = nullptr;
-    size_t n = 0, d = 0;
-    int storage = GPANN_STORAGE_F32;
-    uint32_t id_base = 0;
-    // rows in original order: float [n,d] or bytes [n,d]
-    void* rows = nullptr;
-    size_t pitch = 0;
-    bool owns_rows = true;
-    // norm-sorted tensor layout for byte storage with d <= 128 (topk_tc.cu)
-    unsigned char* t_rows = nullptr;
-    int32_t* t_norms = nullptr;
-    uint32_t* t_ids = nullptr;
-    size_t n_pad = 0;
-    CUtensorMap tmap;
-    bool has_tensor = false;
-    // float storage, d <= 128: norm-sorted bf16 rows [n_pad, dp] + fp32 norms + ids, built lazily by the first
-    // tensor-path query (t_rows / t_norms / t_ids / tmap above are reused for it)
-    int dp = 0;               // padded row length in elements (multiple of 64)
-    bool tensor_tried = false;
-    // float storage, d <= 128: split-precision rows for the tensor k-means assignment (kmeans_tc.cu), built lazily
-    unsigned short* km_rows = nullptr;  // [km_npad, 2*km_dpad] bf16: hi block, lo block
-    float* km_xnorm = nullptr;          // [km_npad] |x| rounded up; [km_npad] holds the maximum
-    size_t km_npad = 0;
-    int km_dpad = 0;
-    CUtensorMap km_tmap;
-    bool km_tried = false, km_ok = false;
-};
-
-namespace {
-
-int fail(gpann_ctx* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
-    return code;
-}
-
-#define CU_TRY(ctx, expr)                                                                                      \
-    do {                                                                                                       \
-        cudaError_t e__ = (expr);                                                                              \
-        if (e__ != cudaSuccess) {                                                                              \
-            return fail(ctx, e__ == cudaErrorMemoryAllocation ? GPANN_E_OOM : GPANN_E_CUDA,                    \
-                        std::string(#expr) + ": " + cudaGetErrorString(e__));                                  \
-        }                                                                                                      \
-    } while (0)
-
-#define GP_TRY(expr)             \
-    do {                         \
-        int r__ = (expr);        \
-        if (r__ != 0) return r__; \
-    } while (0)
-
-int reserve(gpann_ctx* ctx, DevBuf& b, size_t bytes) {
-    if (bytes <= b.cap) return 0;
-    if (b.p) CU_TRY(ctx, cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    const size_t want = std::max(bytes, (size_t) 256);
-    CU_TRY(ctx, cudaMalloc(&b.p, want));
-    b.cap = want;
-    return 0;
-}
-void release(DevBuf& b) {
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-}
-
-int odd16_pitch(int row_bytes) {
-    int p = (row_bytes + 15) & ~15;
-    if (((p >> 4) & 1) == 0) p += 16;
-    return p;
-}
-
-int check_launch(gpann_ctx* ctx, const char* what, int count = 1) {
-    ctx->launches += count;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, GPANN_E_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
-    return 0;
-}
-
-int log2_ceil(size_t x) {
-    int b = 0;
-    while (((size_t) 1 << b) < x) ++b;
-    return b;
-}
-
-int blocks_for(gpann_ctx* ctx, size_t items, int per_block = 256, int waves = 16) {
-    return (int) std::max<size_t>(1, std::min<size_t>((items + per_block - 1) / per_block, (size_t) ctx->num_sms * waves));
-}
+namespace gpimpl {
 
 // Row-major [rows, row_elems] operand matrix, fetched as boxes of box_rows x one 128-byte K block, SWIZZLE_128B.
 int encode_rows_map(gpann_ctx* ctx, CUtensorMap* map, void* base, size_t rows, int box_rows, const char* what,
@@ -168,48 +41,43 @@ int build_tensor_bytes(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
     if (n == 0 || d > tc::kRowBytes || n > 0x7FFFFF00ull) return 0;
     if (!ctx->encode_tiled) return 0;
     const size_t n_pad = ((n + tc::kTileN - 1) / tc::kTileN) * tc::kTileN;
-    uint32_t *norms = nullptr, *index = nullptr, *norms_sorted = nullptr, *perm = nullptr;
-    void* tmp = nullptr;
+    ScopedDev norms, index, norms_sorted, perm, tmp;  // freed on every exit path
     size_t tmp_bytes = 0;
-    auto cleanup = [&]() {
-        cudaFree(norms); cudaFree(index); cudaFree(norms_sorted); cudaFree(perm); cudaFree(tmp);
-    };
-    CU_TRY(ctx, cudaMalloc(&norms, n * 4));
-    if (cudaMalloc(&index, n * 4) != cudaSuccess || cudaMalloc(&norms_sorted, n * 4) != cudaSuccess ||
-        cudaMalloc(&perm, n * 4) != cudaSuccess) {
-        cleanup();
+    if (norms.alloc(n * 4) != cudaSuccess || index.alloc(n * 4) != cudaSuccess || norms_sorted.alloc(n * 4) != cudaSuccess ||
+        perm.alloc(n * 4) != cudaSuccess) {
+        cudaGetLastError();
         return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory");
     }
     const int is_signed = pts->storage == GPANN_STORAGE_S8;
-    launch_byte_norms((const unsigned char*) pts->rows, n, d, pts->pitch, is_signed, norms, index, blocks_for(ctx, n), st);
+    launch_byte_norms((const unsigned char*) pts->rows, n, d, pts->pitch, is_signed, norms.as<uint32_t>(), index.as<uint32_t>(),
+                      ctx->num_sms, st);
     GP_TRY(check_launch(ctx, "byte_norms_kernel"));
-    sort_pairs_u32(nullptr, tmp_bytes, norms, norms_sorted, index, perm, n, 25, st);
-    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) {
-        cleanup();
+    sort_pairs_u32(nullptr, tmp_bytes, norms.as<uint32_t>(), norms_sorted.as<uint32_t>(), index.as<uint32_t>(), perm.as<uint32_t>(), n, 25, st);
+    if (tmp.alloc(tmp_bytes) != cudaSuccess) {
+        cudaGetLastError();
         return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (sort)");
     }
-    if (sort_pairs_u32(tmp, tmp_bytes, norms, norms_sorted, index, perm, n, 25, st) != cudaSuccess) {
-        cleanup();
+    if (sort_pairs_u32(tmp.p, tmp_bytes, norms.as<uint32_t>(), norms_sorted.as<uint32_t>(), index.as<uint32_t>(), perm.as<uint32_t>(), n, 25,
+                       st) != cudaSuccess)
         return fail(ctx, GPANN_E_CUDA, "build_tensor_bytes: radix sort failed");
-    }
     ctx->launches += 4;
     if (cudaMalloc(&pts->t_rows, n_pad * tc::kRowBytes) != cudaSuccess || cudaMalloc(&pts->t_norms, n_pad * 4) != cudaSuccess ||
         cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess) {
-        cleanup();
-        return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (layout)");
+        cudaGetLastError();
+        return fail(ctx, GPANN_E_OOM, "build_tensor_bytes: out of device memory (layout)");  // gpann_points_free releases what was allocated
     }
-    launch_gather_sorted_rows((const unsigned char*) pts->rows, n, d, pts->pitch, perm, norms_sorted, pts->id_base, n_pad,
-                              pts->t_rows, pts->t_norms, pts->t_ids, blocks_for(ctx, n_pad * 32, 256, 32), st);
+    launch_gather_sorted_rows((const unsigned char*) pts->rows, n, d, pts->pitch, perm.as<uint32_t>(), norms_sorted.as<uint32_t>(),
+                              pts->id_base, n_pad, pts->t_rows, pts->t_norms, pts->t_ids, blocks_for(ctx, n_pad * 32, 256, 32), st);
     GP_TRY(check_launch(ctx, "gather_sorted_rows_kernel"));
     CU_TRY(ctx, cudaStreamSynchronize(st));
-    cleanup();
     pts->n_pad = n_pad;
     GP_TRY(encode_rows_map(ctx, &pts->tmap, pts->t_rows, n_pad, tc::kTileN, "points"));
     pts->has_tensor = true;
     return 0;
 }
 
-// Lazily built on the first tensor-path query over a float point set (d <= 128): norm-sorted bf16 rows.
+// Lazily built on the first tensor-path query over a float point set (d <= 128): norm-sorted bf16 rows.  Running out of
+// memory here is not an error of the query: the layout is simply not built and the exact CUDA-core scan serves the set.
 int build_tensor_float(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
     pts->tensor_tried = true;
     const size_t n = pts->n;
@@ -217,37 +85,35 @@ int build_tensor_float(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
     if (n == 0 || d > 64 * tc::kMaxKBlocks || n > 0x7FFFFF00ull || !ctx->encode_tiled) return 0;
     const int dp = ((d + 63) / 64) * 64;
     const size_t n_pad = ((n + tc::kTileN - 1) / tc::kTileN) * tc::kTileN;
-    uint32_t *norms = nullptr, *index = nullptr, *norms_sorted = nullptr, *perm = nullptr;
-    void* tmp = nullptr;
+    ScopedDev norms, index, norms_sorted, perm, tmp;
     size_t tmp_bytes = 0;
-    auto cleanup = [&]() {
-        cudaFree(norms); cudaFree(index); cudaFree(norms_sorted); cudaFree(perm); cudaFree(tmp);
+    auto give_up = [&]() {  // not enough memory: drop what was allocated, keep the point set usable
+        cudaGetLastError();
+        if (pts->t_rows) cudaFree(pts->t_rows);
+        if (pts->t_norms) cudaFree(pts->t_norms);
+        if (pts->t_ids) cudaFree(pts->t_ids);
+        pts->t_rows = nullptr, pts->t_norms = nullptr, pts->t_ids = nullptr;
+        return 0;
     };
-    if (cudaMalloc(&norms, n * 4) != cudaSuccess || cudaMalloc(&index, n * 4) != cudaSuccess ||
-        cudaMalloc(&norms_sorted, n * 4) != cudaSuccess || cudaMalloc(&perm, n * 4) != cudaSuccess) {
-        cleanup();
-        return fail(ctx, GPANN_E_OOM, "build_tensor_float: out of device memory");
-    }
-    launch_float_norms((const float*) pts->rows, n, d, norms, index, blocks_for(ctx, n), st);
+    if (norms.alloc(n * 4) != cudaSuccess || index.alloc(n * 4) != cudaSuccess || norms_sorted.alloc(n * 4) != cudaSuccess ||
+        perm.alloc(n * 4) != cudaSuccess)
+        return give_up();
+    launch_float_norms((const float*) pts->rows, n, d, norms.as<uint32_t>(), index.as<uint32_t>(), blocks_for(ctx, n), st);
     GP_TRY(check_launch(ctx, "float_norms_kernel"));
-    sort_pairs_u32(nullptr, tmp_bytes, norms, norms_sorted, index, perm, n, 32, st);
-    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess ||
-        sort_pairs_u32(tmp, tmp_bytes, norms, norms_sorted, index, perm, n, 32, st) != cudaSuccess) {
-        cleanup();
-        return fail(ctx, GPANN_E_OOM, "build_tensor_float: radix sort failed");
-    }
+    sort_pairs_u32(nullptr, tmp_bytes, norms.as<uint32_t>(), norms_sorted.as<uint32_t>(), index.as<uint32_t>(), perm.as<uint32_t>(), n, 32, st);
+    if (tmp.alloc(tmp_bytes) != cudaSuccess) return give_up();
+    if (sort_pairs_u32(tmp.p, tmp_bytes, norms.as<uint32_t>(), norms_sorted.as<uint32_t>(), index.as<uint32_t>(), perm.as<uint32_t>(), n, 32,
+                       st) != cudaSuccess)
+        return fail(ctx, GPANN_E_CUDA, "build_tensor_float: radix sort failed");
     ctx->launches += 5;
     if (cudaMalloc(&pts->t_rows, n_pad * (size_t) dp * 2) != cudaSuccess || cudaMalloc(&pts->t_norms, n_pad * 4) != cudaSuccess ||
-        cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess) {
-        cleanup();
-        return fail(ctx, GPANN_E_OOM, "build_tensor_float: out of device memory (layout)");
-    }
-    launch_gather_sorted_rows_bf16((const float*) pts->rows, n, d, dp, perm, norms_sorted, pts->id_base, n_pad,
-                                   (unsigned short*) pts->t_rows, (float*) pts->t_norms, pts->t_ids,
+        cudaMalloc(&pts->t_ids, n_pad * 4) != cudaSuccess)
+        return give_up();
+    launch_gather_sorted_rows_bf16((const float*) pts->rows, n, d, dp, perm.as<uint32_t>(), norms_sorted.as<uint32_t>(), pts->id_base,
+                                   n_pad, (unsigned short*) pts->t_rows, (float*) pts->t_norms, pts->t_ids,
                                    blocks_for(ctx, n_pad * 32, 256, 32), st);
     GP_TRY(check_launch(ctx, "gather_sorted_rows_bf16_kernel"));
     CU_TRY(ctx, cudaStreamSynchronize(st));
-    cleanup();
     pts->n_pad = n_pad;
     pts->dp = dp;
     GP_TRY(encode_rows_map(ctx, &pts->tmap, pts->t_rows, n_pad, tc::kTileN, "float points", true, dp));
@@ -256,17 +122,10 @@ int build_tensor_float(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
 }
 
 // ---- top-k dispatch ----------------------------------------------------------------------------------------
-struct TopkOut {
-    uint64_t* keys = nullptr;  // device [nq,k]
-    float* dist = nullptr;     // device [nq,k]
-    uint32_t* id = nullptr;    // device [nq,k]
-    uint32_t* count = nullptr; // device [nq]
-    float* kth = nullptr;      // device [nq]
-    int kth_full_only = 0;
-};
 
+// gate/gate_want: optional device flag -- the merge runs only when (*gate != 0) == gate_want (asynchronous fall-backs).
 int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_stride, size_t nq, int k, const TopkOut& o,
-                 size_t out_q_offset, cudaStream_t st) {
+                 size_t out_q_offset, cudaStream_t st, const int* gate, int gate_want) {
     MergeParams mp;
     mp.keys = keys;
     mp.parts = parts;
@@ -280,13 +139,17 @@ int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_s
     mp.out_count = o.count ? o.count + out_q_offset : nullptr;
     mp.out_kth = o.kth ? o.kth + out_q_offset : nullptr;
     mp.kth_full_only = o.kth_full_only;
+    mp.gate = gate;
+    mp.gate_want = gate_want;
     const size_t smem = (size_t) 4 * mp.cap * sizeof(uint64_t);
     launch_merge_keys(mp, (unsigned) ((nq + 3) / 4), smem, st);
     return check_launch(ctx, "merge_keys_kernel");
 }
 
+// The CUDA-core scan of rows [row_begin,row_end) for nq queries.  Queries are served in batches sized so that the per-CTA
+// partial lists stay inside a fixed scratch budget (the reference's ComputeGroundTruth has no limit on nq or k).
 int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
-                int metric, const TopkOut& out, cudaStream_t st) {
+                int metric, const TopkOut& out, cudaStream_t st, const int* gate, int gate_want) {
     StreamParams p;
     std::memset(&p, 0, sizeof(p));
     p.rows = (const char*) pts->rows;
@@ -299,10 +162,10 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     p.id_base = pts->id_base;
     p.id_lo = 0;
     p.id_hi = 0xFFFFFFFFu;
-    p.queries = dq;
-    p.nq = (int) nq;
     p.k = k;
     p.metric = metric;
+    p.gate = gate;
+    p.gate_want = gate_want;
     const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
     const int row_bytes = p.d * elem;
     p.spitch = odd16_pitch(row_bytes);
@@ -313,7 +176,7 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16;
     const size_t budget = 160 * 1024;
     if (tile_bytes + per_q > 200 * 1024)
-        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile");
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile (f32: d <= 384)");
     const int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16),
                                           std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
     p.qb = qb;
@@ -321,19 +184,31 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     const size_t nrows = row_end - row_begin;
     const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
-    const unsigned gx = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
-    const unsigned gy = (unsigned) ((nq + qb - 1) / qb);
-    GP_TRY(reserve(ctx, ctx->partial, (size_t) gx * nq * k * sizeof(uint64_t)));
+    unsigned gx = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
+    // a gated launch is normally a no-op (every CTA reads the flag and returns): keep its grid, and its scratch, small
+    if (gate) gx = std::min<unsigned>(gx, (unsigned) ctx->num_sms);
+    // queries per launch: gx * nq_l * k keys of partial lists within ~256 MB (at least one shared-memory batch)
+    const size_t scratch_budget = (size_t) 256 << 20;
+    const size_t nq_launch = std::max<size_t>(qb, std::min<size_t>(nq, scratch_budget / ((size_t) gx * k * sizeof(uint64_t)) / qb * qb));
+    GP_TRY(reserve(ctx, ctx->partial, (size_t) gx * nq_launch * k * sizeof(uint64_t)));
     p.partial = (uint64_t*) ctx->partial.p;
-    if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-    launch_topk_stream(p, dim3(gx, gy), smem, st);
-    if (ctx->timing) {
-        cudaEventRecord(ctx->ev1, st);
-        ctx->timed = true;
+    for (size_t q0 = 0; q0 < nq; q0 += nq_launch) {
+        const size_t nq_l = std::min(nq_launch, nq - q0);
+        p.queries = dq + q0 * pts->d;
+        p.nq = (int) nq_l;
+        const unsigned gy = (unsigned) std::min<size_t>((nq_l + qb - 1) / qb, gate ? 4 : 32768);
+        const bool time_it = ctx->timing && q0 == 0;
+        if (time_it) cudaEventRecord(ctx->ev0, st);
+        launch_topk_stream(p, dim3(gx, gy), smem, st);
+        if (time_it) {
+            cudaEventRecord(ctx->ev1, st);
+            ctx->timed = true;
+        }
+        GP_TRY(check_launch(ctx, "topk_stream_kernel"));
+        GP_TRY(launch_merge(ctx, p.partial, gx, nq_l, nq_l, k, out, q0, st, gate, gate_want));
     }
-    GP_TRY(check_launch(ctx, "topk_stream_kernel"));
-    ctx->last_algo = "stream";
-    return launch_merge(ctx, p.partial, gx, nq, nq, k, out, 0, st);
+    if (!gate) ctx->last_algo = "stream";
+    return 0;
 }
 
 // ---- the tcgen05 path: byte storage (exact int32 distances) or float storage (bf16 filter + exact fp32 re-rank) ----
@@ -353,15 +228,18 @@ struct TcPlan {
     int is_signed = 0, d = 0, dp = 0, kblocks = 1, max_r = tc::kMaxR, stages = 3, qcap = 1024;
     int R = 1, G = 1, k = 0, cap = 128, lists_smem = 0;
     size_t nqb = 0, nq_pad = 0;
+    const int* gate = nullptr;  // device flag the batch's kernels are gated on (byte storage: queries integer-valued)
     CUtensorMap tmap_q;
 };
 
 size_t tc_batch_max(const gpann_ctx* ctx, int kblocks) { return (size_t) ctx->num_sms * (kblocks == 1 ? tc::kMaxR : 2) * tc::kTileM; }
 
-// Prepare one batch of nqb <= tc_batch_max queries.  *ok = 0 (and nothing else done) when byte points meet queries
-// that are not integer-valued in the storage's range; the caller then takes the exact float scan.
-int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, const float* dq, size_t nqb, int k, cudaStream_t st,
-                       int* ok) {
+constexpr int kFlagQueriesOk = 4;  // ctx->flags[4]: non-zero = the prepared queries are integer-valued in the storage range
+
+// Prepare one batch of nqb <= tc_batch_max queries (asynchronous).  For byte storage the kernel clears
+// ctx->flags[kFlagQueriesOk] when a query coordinate is not an integer in the storage's range; every tensor-path kernel of
+// the batch is gated on that flag (pl.gate) and the caller queues the exact float scan behind it, gated the other way.
+void tc_plan_shape(TcPlan& pl, int storage, int d, int dp, size_t nqb, int k) {
     pl.is_float = storage == GPANN_STORAGE_F32;
     pl.is_signed = storage == GPANN_STORAGE_S8;
     pl.d = d;
@@ -392,7 +270,11 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
     pl.G = (int) ((nqb + (size_t) pl.R * tc::kTileM - 1) / ((size_t) pl.R * tc::kTileM));
     pl.nq_pad = (size_t) pl.G * pl.R * tc::kTileM;
     pl.cap = std::max(128, pow2_ceil(k + 64));
-    *ok = 1;
+    pl.gate = nullptr;
+}
+
+int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, const float* dq, size_t nqb, int k, cudaStream_t st) {
+    tc_plan_shape(pl, storage, d, dp, nqb, k);
     const size_t qrow_bytes = pl.is_float ? (size_t) dp * 2 : tc::kRowBytes;
     GP_TRY(reserve(ctx, ctx->qrows, pl.nq_pad * qrow_bytes));
     GP_TRY(reserve(ctx, ctx->qnorm, pl.nq_pad * 4));
@@ -404,40 +286,38 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
                                  (float*) ctx->qf32.p, (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
         GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
     } else {
-        int one = 1;
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, &one, 4, cudaMemcpyHostToDevice, st));
+        int* okflag = (int*) ctx->flags.p + kFlagQueriesOk;
+        CU_TRY(ctx, cudaMemsetAsync(okflag, 1, sizeof(int), st));  // 0x01010101: "ok" until a query refutes it
         launch_prep_queries_bytes(dq, (int) nqb, d, (int) pl.nq_pad, pl.is_signed, (unsigned char*) ctx->qrows.p,
-                                  (int32_t*) ctx->qnorm.p, (int*) ctx->flags.p,
+                                  (int32_t*) ctx->qnorm.p, okflag,
                                   (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
         GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
-        int okh = 0;
-        CU_TRY(ctx, cudaMemcpyAsync(&okh, ctx->flags.p, 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        if (!okh) {
-            *ok = 0;
-            return 0;
-        }
+        pl.gate = okflag;
     }
     return encode_rows_map(ctx, &pl.tmap_q, ctx->qrows.p, pl.nq_pad, tc::kTileM, "queries", pl.is_float,
                            pl.is_float ? dp : tc::kRowBytes);
 }
 
-// Scan one layout for the prepared batch.  The per-split partial lists land in ctx->partial [1 + S, nq_pad, k] (parts
-// 1..S); with `carry` part 0 holds the running result of earlier chunks (and receives the merged one, together with
-// the tightened per-query bounds); otherwise the merged result of the S parts goes to `out` at query offset q_off.
-int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass, bool carry, bool carry_init, const TopkOut& out,
-            size_t q_off, cudaStream_t st) {
-    const int k = pl.k;
-    const uint32_t tiles_total = (uint32_t) (lay.n_pad / tc::kTileN);
-    const int S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / pl.G), tiles_total));
-    const int S_max = std::max(1, ctx->num_sms / pl.G);
-    const size_t part_keys = pl.nq_pad * (size_t) k;
-    GP_TRY(reserve(ctx, ctx->cand, (size_t) pl.G * S * pl.R * tc::kTileM * pl.cap * sizeof(uint64_t)));
-    GP_TRY(reserve(ctx, ctx->partial, (size_t) (S_max + 1) * part_keys * sizeof(uint64_t)));
-    uint64_t* carry_keys = (uint64_t*) ctx->partial.p;  // part 0: the running result; the splits write parts 1..S
-    uint64_t* partial = carry_keys + part_keys;
-    if (carry && carry_init) CU_TRY(ctx, cudaMemsetAsync(carry_keys, 0xFF, part_keys * sizeof(uint64_t), st));
+// Launch geometry + kernel arguments shared by the sample passes and the main pass over one layout.
+struct TcLaunch {
     tc::Args a;
+    int S = 1, S_max = 1;
+    unsigned grid = 1;
+    size_t smem = 0, part_keys = 0;
+    uint32_t tiles_total = 0;
+    uint64_t* carry_keys = nullptr;  // ctx->partial part 0
+};
+
+int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L) {
+    const int k = pl.k;
+    L.tiles_total = (uint32_t) (lay.n_pad / tc::kTileN);
+    L.S = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (ctx->num_sms / pl.G), L.tiles_total));
+    L.S_max = std::max(1, ctx->num_sms / pl.G);
+    L.part_keys = pl.nq_pad * (size_t) k;
+    if (!pl.lists_smem) GP_TRY(reserve(ctx, ctx->cand, (size_t) pl.G * L.S * pl.R * tc::kTileM * pl.cap * sizeof(uint64_t)));
+    GP_TRY(reserve(ctx, ctx->partial, (size_t) (L.S_max + 1) * L.part_keys * sizeof(uint64_t)));
+    L.carry_keys = (uint64_t*) ctx->partial.p;  // part 0: the running result; the splits write parts 1..S
+    tc::Args& a = L.a;
     std::memset(&a, 0, sizeof(a));
     a.pnorm = lay.norms;
     a.pid = lay.ids;
@@ -446,7 +326,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.nq = (int) pl.nqb;
     a.R = pl.R;
     a.G = pl.G;
-    a.S = S;
+    a.S = L.S;
     a.nks = pl.is_float ? (pl.d + 15) / 16 : (pl.d + 31) / 32;
     a.kblocks = pl.kblocks;
     a.stages = pl.stages;
@@ -456,7 +336,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.lists_smem = pl.lists_smem;
     a.idesc = pl.is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(pl.is_signed);
     a.cand = (uint64_t*) ctx->cand.p;
-    a.partial = partial;
+    a.partial = L.carry_keys + L.part_keys;
     a.bound = (uint32_t*) ctx->bound.p;
     a.mode = ctx->tc_mode;
     a.rows_f32 = pl.is_float ? lay.rows_f32 : nullptr;
@@ -464,62 +344,84 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
     a.d = pl.d;
     a.id_base = lay.id_base;
     a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
-    const unsigned grid = (unsigned) (pl.G * S);
-    const size_t smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
-    // Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the
-    // final ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one
-    // (a cold start pushes EVERY distance through the selection warps).  Three levels: 1 tile per split (cold, but
-    // tiny), then 12 and 160 tiles per split, each filtered by the previous level's bound.  (During a pass the CTAs of
-    // different point splits also share their k-th distances through a.bound, see publish_threshold.)
-    if (prepass && ctx->tc_prepass && ctx->tc_mode == 0 && !(ctx->tc_warm && ctx->tc_warm_valid)) {
-        // level sizes follow the shard: a third level of 160 tiles per split is 8 % of a 12.5M-row shard's work
-        const uint32_t per_split_tiles = tiles_total / (uint32_t) S;
-        uint32_t l3 = std::min(160u, per_split_tiles / 96u);
-        if (l3 < 24u) l3 = 0;  // small splits: two levels (measured: a third costs more than it saves at 1M points)
-        uint32_t levels[3] = { 1, l3 ? std::max(4u, std::min(12u, l3 / 12u)) : 12u, l3 };
-        static const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment knob: "a/b/c" tiles per split (0 = skip the level)
-        if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
-        for (uint32_t per_split : levels) {
-            if (per_split == 0) continue;
-            const uint32_t nsample = (uint32_t) S * per_split;
-            if (tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
-            a.ntiles = nsample;
-            a.tile_stride = tiles_total / nsample;
-            a.tile_lo = a.tile_stride / 2;
-            a.sample_pass = 1;
-            static const char* e_sst = std::getenv("GPANN_TC_STATS");
-            if (e_sst && std::atoi(e_sst) >= 2) {
-                GP_TRY(reserve(ctx, ctx->misc, 256));
-                CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
-                a.stats = (unsigned long long*) ctx->misc.p;
-            }
-            launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
-            GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
-            if (a.stats) {
-                unsigned long long h[32] = { 0 };
-                cudaStreamSynchronize(st);
-                cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
-                std::fprintf(stderr, "[gpann stats] sample pass %u tiles/split: CTA 0 clk: filter loop done %llu, selection drained %llu, final selection done %llu; "
-                                     "records %llu; mma thread clk %llu | CTA 0 selection warp 0: %llu batches, %llu rounds, insert clk %llu, pop clk %llu, idle polls %llu | slowest CTA: set-up %llu, filter loop %llu, whole kernel %llu clk\n",
-                             per_split, h[10], h[11], h[12], h[0], h[2] / grid, h[16], h[17], h[18], h[20], h[19], h[22], h[23], h[21]);
-                a.stats = nullptr;
-            }
-            TopkOut b;
-            b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
-            b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
-            GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st));
+    a.gate = pl.gate;
+    L.grid = (unsigned) (pl.G * L.S);
+    L.smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
+    return 0;
+}
+
+// Pre-passes over strided samples of tiles: the k-th distances found on a sample are valid upper bounds on the final
+// ones and let every CTA of the next pass start with a tight filter threshold instead of a cold one (a cold start pushes
+// EVERY distance through the selection warps).  Up to three levels: 1 tile per split (cold, but tiny), then ~12 and ~160
+// tiles per split, each filtered by the previous level's bound.  The bounds land in ctx->bound [nq_pad] (float bits);
+// a sharded caller all-reduces them (min) across its ranks before the main pass (multi.cu).
+int tc_sample(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, cudaStream_t st) {
+    if (!ctx->tc_prepass || ctx->tc_mode != 0 || (ctx->tc_warm && ctx->tc_warm_valid)) return 0;
+    TcLaunch L;
+    GP_TRY(tc_setup(ctx, pl, lay, L));
+    tc::Args& a = L.a;
+    const int S = L.S, k = pl.k;
+    // level sizes follow the shard: a third level of 160 tiles per split is 8 % of a 12.5M-row shard's work
+    const uint32_t per_split_tiles = L.tiles_total / (uint32_t) S;
+    uint32_t l3 = std::min(160u, per_split_tiles / 96u);
+    if (l3 < 24u) l3 = 0;  // small splits: two levels (measured: a third costs more than it saves at 1M points)
+    uint32_t levels[3] = { 1, l3 ? std::max(4u, std::min(12u, l3 / 12u)) : 12u, l3 };
+    const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment / test knob: "a/b/c" tiles per split (0 = skip the level)
+    if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
+    for (uint32_t per_split : levels) {
+        if (per_split == 0) continue;
+        const uint32_t nsample = (uint32_t) S * per_split;
+        if (L.tiles_total < 32u * nsample || (size_t) nsample * tc::kTileN < (size_t) 4 * k) continue;
+        a.ntiles = nsample;
+        a.tile_stride = L.tiles_total / nsample;
+        a.tile_lo = a.tile_stride / 2;
+        a.sample_pass = 1;
+        static const char* e_sst = std::getenv("GPANN_TC_STATS");
+        if (e_sst && std::atoi(e_sst) >= 2) {
+            GP_TRY(reserve(ctx, ctx->misc, 256));
+            CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
+            a.stats = (unsigned long long*) ctx->misc.p;
         }
+        launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, L.grid, L.smem, st);
+        GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
+        if (a.stats) {
+            unsigned long long h[32] = { 0 };
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "[gpann stats] sample pass %u tiles/split: CTA 0 clk: filter loop done %llu, selection drained %llu, final selection done %llu; "
+                                 "records %llu; mma thread clk %llu | CTA 0 selection warp 0: %llu batches, %llu rounds, insert clk %llu, pop clk %llu, idle polls %llu | slowest CTA: set-up %llu, filter loop %llu, whole kernel %llu clk\n",
+                         per_split, h[10], h[11], h[12], h[0], h[2] / L.grid, h[16], h[17], h[18], h[20], h[19], h[22], h[23], h[21]);
+            a.stats = nullptr;
+        }
+        TopkOut b;
+        b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
+        b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
+        GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st, pl.gate, 1));
     }
+    return 0;
+}
+
+// The full pass over one layout for the prepared batch.  The per-split partial lists land in ctx->partial
+// [1 + S, nq_pad, k] (parts 1..S); with `carry` part 0 holds the running result of earlier chunks (and receives the merged
+// one, together with the tightened per-query bounds); otherwise the merged result of the S parts goes to `out` at query
+// offset q_off.
+int tc_main(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool carry, bool carry_init, const TopkOut& out, size_t q_off,
+            cudaStream_t st) {
+    TcLaunch L;
+    GP_TRY(tc_setup(ctx, pl, lay, L));
+    tc::Args& a = L.a;
+    const int S = L.S, k = pl.k;
+    if (carry && carry_init) CU_TRY(ctx, cudaMemsetAsync(L.carry_keys, 0xFF, L.part_keys * sizeof(uint64_t), st));
     a.tile_lo = 0;
     a.tile_stride = 1;
-    a.ntiles = tiles_total;
+    a.ntiles = L.tiles_total;
     a.sample_pass = 0;
     static const bool no_pace = std::getenv("GPANN_TC_NOPACE") != nullptr;
     const char* e_pw = std::getenv("GPANN_TC_PACE_WINDOW");  // tests: a tight window exercises the pacing protocol on small sets
     a.pace_window = e_pw ? (uint32_t) std::max(1, std::atoi(e_pw)) : tc::kPaceWindow;
-    if (!no_pace && tiles_total / S >= 4 * a.pace_window && pl.G > 1 && (int) grid <= ctx->num_sms) {  // all CTAs co-resident
-        GP_TRY(reserve(ctx, ctx->pace, (size_t) grid * sizeof(uint32_t)));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->pace.p, 0, (size_t) grid * sizeof(uint32_t), st));
+    if (!no_pace && L.tiles_total / S >= 4 * a.pace_window && pl.G > 1 && (int) L.grid <= ctx->num_sms) {  // all CTAs co-resident
+        GP_TRY(reserve(ctx, ctx->pace, (size_t) L.grid * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->pace.p, 0, (size_t) L.grid * sizeof(uint32_t), st));
         a.pace = (uint32_t*) ctx->pace.p;
     }
     static const bool want_stats = std::getenv("GPANN_TC_STATS") != nullptr;
@@ -529,7 +431,7 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
         a.stats = (unsigned long long*) ctx->misc.p;
     }
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
-    launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, grid, smem, st);
+    launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, L.grid, L.smem, st);
     if (ctx->timing) {
         cudaEventRecord(ctx->ev1, st);
         ctx->timed = true;
@@ -539,8 +441,8 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
         unsigned long long h[32] = { 0 };
         cudaStreamSynchronize(st);
         cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
-        const double g = (double) grid, items = (double) tiles_total / S * pl.R * tc::kHalves;
-        std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u, %.0f items/CTA\n", h[0], h[1], grid, items);
+        const double g = (double) L.grid, items = (double) L.tiles_total / S * pl.R * tc::kHalves;
+        std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u, %.0f items/CTA\n", h[0], h[1], L.grid, items);
         std::fprintf(stderr, "[gpann stats] clk per item (CTA average): MMA thread total %.0f = wait operands %.0f + wait TMEM slot %.0f + issue %.0f | "
                              "filter warp 0 total %.0f = wait accumulator %.0f + wait tile %.0f + work %.0f | TMA thread total %.0f, wait free stage %.0f\n",
                      h[2] / g / items, h[3] / g / items, h[4] / g / items, (h[2] - h[3] - h[4]) / g / items, h[5] / g / items, h[6] / g / items,
@@ -551,40 +453,53 @@ int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass,
             TopkOut b;
             b.kth = (float*) ctx->bound.p;
             b.kth_full_only = 1;
-            GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st));
+            GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st, pl.gate, 1));
             ctx->tc_warm_valid = true;
         }
-        return launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, out, q_off, st);
+        return launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, out, q_off, st, pl.gate, 1);
     }
     TopkOut c;
-    c.keys = carry_keys;              // in place: a warp reads all parts of its query before it writes
+    c.keys = L.carry_keys;            // in place: a warp reads all parts of its query before it writes
     c.kth = (float*) ctx->bound.p;
     c.kth_full_only = 1;
-    return launch_merge(ctx, carry_keys, S + 1, pl.nq_pad, pl.nqb, k, c, 0, st);
+    return launch_merge(ctx, L.carry_keys, S + 1, pl.nq_pad, pl.nqb, k, c, 0, st, pl.gate, 1);
 }
 
-int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out,
-                cudaStream_t st, int* queries_ok_host) {
-    const bool is_float = pts->storage == GPANN_STORAGE_F32;
-    const int d = (int) pts->d;
-    const size_t batch_max = tc_batch_max(ctx, is_float ? pts->dp / 64 : 1);
+int tc_scan(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool prepass, bool carry, bool carry_init, const TopkOut& out,
+            size_t q_off, cudaStream_t st) {
+    if (prepass) GP_TRY(tc_sample(ctx, pl, lay, st));
+    return tc_main(ctx, pl, lay, carry, carry_init, out, q_off, st);
+}
+
+TcLayout layout_of(const gpann_points* pts) {
     TcLayout lay;
     lay.tmap = &pts->tmap;
     lay.norms = pts->t_norms;
     lay.ids = pts->t_ids;
     lay.n_pad = pts->n_pad;
-    lay.rows_f32 = is_float ? (const float*) pts->rows : nullptr;
+    lay.rows_f32 = pts->storage == GPANN_STORAGE_F32 ? (const float*) pts->rows : nullptr;
     lay.id_base = pts->id_base;
-    *queries_ok_host = 1;
+    return lay;
+}
+
+// All query batches of one call on the tensor path (asynchronous).  *gate receives the device flag the byte path's kernels
+// were gated on (nullptr for float storage): the caller queues the exact float scan behind, gated the other way.
+// `between` (optional) runs between the sample passes and the main pass of every batch: the sharded entry points
+// all-reduce the per-query bounds across their ranks there.
+int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out, cudaStream_t st,
+                const int** gate, const BetweenFn& between) {
+    const bool is_float = pts->storage == GPANN_STORAGE_F32;
+    const int d = (int) pts->d;
+    const size_t batch_max = tc_batch_max(ctx, is_float ? pts->dp / 64 : 1);
+    const TcLayout lay = layout_of(pts);
+    *gate = nullptr;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
         TcPlan pl;
-        int ok = 1;
-        GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st, &ok));
-        if (!ok) {
-            *queries_ok_host = 0;
-            return 0;
-        }
-        GP_TRY(tc_scan(ctx, pl, lay, true, false, false, out, q0, st));
+        GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st));
+        *gate = pl.gate;
+        GP_TRY(tc_sample(ctx, pl, lay, st));
+        if (between) GP_TRY(between((uint32_t*) ctx->bound.p, pl.nqb, st));  // real queries only: the count every rank agrees on
+        GP_TRY(tc_main(ctx, pl, lay, false, false, out, q0, st));
     }
     ctx->last_algo = is_float ? "tensor_bf16" : (pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8");
     return 0;
@@ -597,7 +512,6 @@ int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t
 // Host rows are bytes (u8/s8) or floats; float rows that hold byte values (the reference's reader widens .u8bin/.i8bin
 // to float, src/points_io.cpp:63-111) are narrowed on the device chunk by chunk and take the exact integer kernel,
 // other float rows take the bf16 filter + exact fp32 re-rank against the raw chunk.
-enum HostKind { kHostU8 = 0, kHostS8 = 1, kHostF32 = 2 };
 
 int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int storage, size_t n, size_t d, uint32_t id_base,
                      const float* dq, size_t nq, int k, size_t chunk_rows, const TopkOut& out, cudaStream_t st) {
@@ -664,7 +578,12 @@ int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int s
         GP_TRY(reserve(ctx, ctx->st_tmp, tmp_bytes));
         TcPlan pl;
         int ok = 1;
-        GP_TRY(tc_prepare_queries(ctx, pl, storage, (int) d, dp, dq, nq, k, st, &ok));
+        GP_TRY(tc_prepare_queries(ctx, pl, storage, (int) d, dp, dq, nq, k, st));
+        if (pl.gate) {  // byte scan: the one synchronisation of the streamed path decides between the integer and the float scan
+            CU_TRY(ctx, cudaMemcpyAsync(&ok, pl.gate, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            pl.gate = nullptr;  // decided on the host: no gating inside the chunk loop
+        }
         if (!ok) {
             if (!host_f32) return fail(ctx, GPANN_E_UNSUPPORTED, "topk_stream: queries are not integer-valued in the storage range");
             storage = GPANN_STORAGE_F32;  // byte-valued points, fractional queries: exact float path
@@ -704,7 +623,7 @@ int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int s
             }
             if (rows_c) {
                 if (is_float) launch_float_norms((const float*) raw, rows_c, (int) d, ka, va, blocks_for(ctx, rows_c), st);
-                else launch_byte_norms(bytes, rows_c, (int) d, d, is_signed, ka, va, blocks_for(ctx, rows_c), st);
+                else launch_byte_norms(bytes, rows_c, (int) d, d, is_signed, ka, va, ctx->num_sms, st);
                 GP_TRY(check_launch(ctx, "norms_kernel"));
                 size_t tb = ctx->st_tmp.cap;
                 if (sort_pairs_u32(ctx->st_tmp.p, tb, ka, kb, va, vb, rows_c, sort_bits, st) != cudaSuccess)
@@ -735,7 +654,7 @@ int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int s
             }
         }
         ctx->last_algo = is_float ? "tensor_bf16_stream" : (is_signed ? "tensor_s8_stream" : "tensor_u8_stream");
-        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, pl.nq_pad, nq, k, out, 0, st);
+        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, pl.nq_pad, nq, k, out, 0, st, nullptr, 0);
     }
 }
 
@@ -747,6 +666,7 @@ int topk_stream_host_api(gpann_ctx* ctx, const void* host_rows, int host_kind, i
     if (k < 1 || k > 448) return fail(ctx, GPANN_E_ARG, "topk_stream: k must be in [1,448]");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    OrderScope order(ctx, st);
     GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
     GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
     GP_TRY(reserve(ctx, ctx->id_out, nq * k * 4));
@@ -766,8 +686,16 @@ int topk_stream_host_api(gpann_ctx* ctx, const void* host_rows, int host_kind, i
     return 0;
 }
 
+// Is the tensor path the one a call of this SHAPE takes?  Depends only on values every shard of a sharded call agrees on
+// (storage, d, nq, k, metric, algo, full range) -- not on the local row count -- so that all ranks of a communicator
+// issue the same sequence of collectives (multi.cu).
+bool tensor_shape(const gpann_ctx* ctx, int storage, size_t d, size_t nq, int k, int metric, bool full) {
+    const bool is_float = storage == GPANN_STORAGE_F32;
+    if (metric != GPANN_METRIC_L2 || !full || k > 448 || d > (size_t) (is_float ? 64 * tc::kMaxKBlocks : tc::kRowBytes)) return false;
+    return ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16);
+}
 int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
-                  int metric, const TopkOut& out, cudaStream_t st) {
+                  int metric, const TopkOut& out, cudaStream_t st, const BetweenFn& between) {
     if (!pts || pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "topk: point set does not belong to this context");
     if (k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "topk: k must be in [1,512]");
     if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(ctx, GPANN_E_ARG, "topk: bad metric");
@@ -775,30 +703,45 @@ int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, siz
     if (nq == 0) return 0;
     const bool full = row_begin == 0 && row_end == pts->n;
     const bool is_float = pts->storage == GPANN_STORAGE_F32;
-    const bool want_tensor = metric == GPANN_METRIC_L2 && full && k <= 448 &&
-                             (ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16 && (!is_float || pts->n >= 4096)));
+    const bool shape_ok = tensor_shape(ctx, pts->storage, pts->d, nq, k, metric, full);
+    // small float sets are not worth a layout -- unless a sharded call needs every rank on the same path
+    const bool want_tensor = shape_ok && (ctx->algo == GPANN_ALGO_TENSOR || !is_float || pts->n >= 4096 || between);
     if (want_tensor && is_float && !pts->tensor_tried)  // lazily build the bf16 layout (handle state, not query state)
         GP_TRY(build_tensor_float(ctx, const_cast<gpann_points*>(pts), st));
     const bool tensor_ok = want_tensor && pts->has_tensor;
     if (ctx->algo == GPANN_ALGO_TENSOR && !tensor_ok)
         return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs d<=128, L2, full range, k<=448");
+    const int* gate = nullptr;
     if (tensor_ok) {
-        int ok = 1;
-        GP_TRY(topk_tensor(ctx, pts, dq, nq, k, out, st, &ok));
-        if (ok) return 0;
-        if (ctx->algo == GPANN_ALGO_TENSOR)
-            return fail(ctx, GPANN_E_UNSUPPORTED, "topk: queries are not integer-valued in the storage range");
+        GP_TRY(topk_tensor(ctx, pts, dq, nq, k, out, st, &gate, between));
+        if (!gate) return 0;
+        ctx->gate_used = true;  // float storage: nothing can refute the tensor path
+        // byte storage: the exact float scan is queued behind, gated on "queries were NOT integer-valued" -- normally every
+        // CTA of it returns at once.  Nothing synchronises: the call stays asynchronous on `st`.
+    } else if (between && shape_ok) {
+        // a rank of a sharded call without a local layout (empty shard, no memory for it): the same bound exchange as the
+        // ranks on the tensor path (one per call: the sharded caller keeps nq within one batch), contributing "no bound"
+        GP_TRY(reserve(ctx, ctx->bound, nq * 4));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->bound.p, 0x7f, nq * 4, st));  // 0x7f7f7f7f: a huge finite float
+        GP_TRY(between((uint32_t*) ctx->bound.p, nq, st));
     }
     if (row_end == row_begin) {
         // empty scan: all-empty output
-        std::vector<uint64_t> e(nq * k, kEmptyKey);
-        GP_TRY(reserve(ctx, ctx->partial, e.size() * 8));
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->partial.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
+        GP_TRY(reserve(ctx, ctx->partial, nq * (size_t) k * 8));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->partial.p, 0xFF, nq * (size_t) k * 8, st));
         ctx->last_algo = "empty";
-        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, nq, nq, k, out, 0, st);
+        return launch_merge(ctx, (const uint64_t*) ctx->partial.p, 1, nq, nq, k, out, 0, st, nullptr, 0);
     }
-    return topk_stream(ctx, pts, row_begin, row_end, dq, nq, k, metric, out, st);
+    return topk_stream(ctx, pts, row_begin, row_end, dq, nq, k, metric, out, st, gate, 0);
+}
+
+// Host-side check after a synchronised call: did byte points meet fractional queries (the gated float scan served them)?
+int queries_were_integer(gpann_ctx* ctx, cudaStream_t st, int* ok) {
+    *ok = 1;
+    if (!ctx->flags.p) return 0;
+    CU_TRY(ctx, cudaMemcpyAsync(ok, (const int*) ctx->flags.p + kFlagQueriesOk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
 }
 
 int topk_host(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries, size_t nq, int k,
@@ -809,6 +752,7 @@ int topk_host(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t 
     if (k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "topk: k must be in [1,512]");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    OrderScope order(ctx, st);
     const size_t d = pts->d;
     GP_TRY(reserve(ctx, ctx->qdev, nq * d * 4));
     GP_TRY(reserve(ctx, ctx->dist_out, nq * k * 4));
@@ -820,12 +764,19 @@ int topk_host(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t 
     o.id = out_id ? (uint32_t*) ctx->id_out.p : nullptr;
     o.count = out_count ? (uint32_t*) ctx->cnt_out.p : nullptr;
     o.kth = out_kth ? (float*) ctx->cnt_out.p + nq : nullptr;
-    GP_TRY(topk_dispatch(ctx, pts, row_begin, row_end, (const float*) ctx->qdev.p, nq, k, metric, o, st));
+    ctx->gate_used = false;
+    GP_TRY(topk_dispatch(ctx, pts, row_begin, row_end, (const float*) ctx->qdev.p, nq, k, metric, o, st, nullptr));
     if (out_dist) CU_TRY(ctx, cudaMemcpyAsync(out_dist, o.dist, nq * k * 4, cudaMemcpyDeviceToHost, st));
     if (out_id) CU_TRY(ctx, cudaMemcpyAsync(out_id, o.id, nq * k * 4, cudaMemcpyDeviceToHost, st));
     if (out_count) CU_TRY(ctx, cudaMemcpyAsync(out_count, o.count, nq * 4, cudaMemcpyDeviceToHost, st));
     if (out_kth) CU_TRY(ctx, cudaMemcpyAsync(out_kth, o.kth, nq * 4, cudaMemcpyDeviceToHost, st));
+    int ok = 1;
+    if (ctx->gate_used) GP_TRY(queries_were_integer(ctx, st, &ok));
     CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (!ok) {  // byte points, fractional queries: the gated exact float scan produced the result
+        if (ctx->algo == GPANN_ALGO_TENSOR) return fail(ctx, GPANN_E_UNSUPPORTED, "topk: queries are not integer-valued in the storage range");
+        ctx->last_algo = "stream";
+    }
     return 0;
 }
 
@@ -870,7 +821,7 @@ int build_kmeans_layout(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st) {
 
 // NearestCenters on the tensor cores (kmeans_tc.cu): split-precision filter + exact re-rank of ambiguous points.
 int kmeans_assign_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int32_t* d_assign,
-                         cudaStream_t st) {
+                         const unsigned char* d_alive, cudaStream_t st) {
     const int d = (int) pts->d, dpad = pts->km_dpad, nkb = dpad / 32;
     // shared memory: NB centroids resident (4*dpad bytes each) + a ring of point tiles (128 rows x 4*dpad bytes)
     int NB = 256, stages = 3;
@@ -896,7 +847,7 @@ int kmeans_assign_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* d
     launch_split_rows_bf16(d_centroids, kc, d, dpad, kc_pad, (unsigned short*) ctx->km_cent.p, nullptr, (float*) ctx->km_hn.p, scal,
                            scal + 1, blocks_for(ctx, kc_pad * 32, 256, 4), st);
     GP_TRY(check_launch(ctx, "split_rows_bf16_kernel(centroids)"));
-    launch_kmeans_centroid_consts(pts->km_xnorm + n_pad, scal, scal + 1, (float*) ctx->km_hn.p, (int) kc, (int) kc_pad, consts, st);
+    launch_kmeans_centroid_consts(pts->km_xnorm + n_pad, scal, scal + 1, (float*) ctx->km_hn.p, (int) kc, (int) kc_pad, d_alive, consts, st);
     GP_TRY(check_launch(ctx, "kmeans_centroid_consts_kernel"));
     CUtensorMap tmap_b;
     GP_TRY(encode_rows_map_sw64(ctx, &tmap_b, ctx->km_cent.p, kc_pad, 2 * dpad, NB, "k-means centroids"));
@@ -937,6 +888,7 @@ int kmeans_assign_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* d
     fp.amb_list = (uint32_t*) ctx->km_amb_list.p;
     fp.amb_count = (uint32_t*) (scal + 2);
     fp.amb_info = (uint2*) ctx->km_amb_info.p;
+    fp.alive = d_alive;
     launch_kmeans_finalize(fp, blocks_for(ctx, pts->n, 256, 8), st);
     GP_TRY(check_launch(ctx, "kmeans_finalize_kernel"));
     launch_kmeans_resolve(fp, ctx->num_sms * 8, st);
@@ -956,16 +908,33 @@ RowsView rows_view(const gpann_points* pts) {
     return v;
 }
 
+// Can the tcgen05 assignment kernel serve this shape?  (NB centroids resident per CTA, CS = kc_pad / NB splits <= SMs.)
+bool kmeans_tensor_fits(const gpann_ctx* ctx, int dpad, size_t kc) {
+    const int nkb = dpad / 32;
+    int NB = 256, stages = 3;
+    while (kmtc::smem_bytes(NB, nkb, stages) > 225 * 1024) {
+        if (stages > 2) --stages;
+        else if (NB > 128) { NB = 128; stages = 3; }
+        else return false;
+    }
+    if (kc <= 128) NB = 128;
+    return (kc + NB - 1) / NB <= (size_t) ctx->num_sms;
+}
+
 int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric,
-                         int32_t* d_assign, float* d_mindist, cudaStream_t st) {
+                         int32_t* d_assign, float* d_mindist, const unsigned char* d_alive, cudaStream_t st) {
     // tensor path: float rows, L2, d <= 128, no per-point distance requested; AUTO takes it when the contraction is big
-    // enough to pay for the layout (n*kc >= 2^24 and at least 32 centroids)
+    // enough to pay for the layout (n*kc >= 2^24 and at least 32 centroids) and the shape fits the kernel -- otherwise,
+    // and when the layout could not be built (memory), the CUDA-core kernel serves the call
     const bool tensor_shape = pts->storage == GPANN_STORAGE_F32 && metric == GPANN_METRIC_L2 && pts->d <= 128 && !d_mindist &&
                               pts->n > 0;
-    const bool want_tensor = tensor_shape && (ctx->algo == GPANN_ALGO_TENSOR ||
-                                              (ctx->algo == GPANN_ALGO_AUTO && kc >= 32 && pts->n * kc >= ((size_t) 1 << 24)));
+    bool want_tensor = tensor_shape && (ctx->algo == GPANN_ALGO_TENSOR ||
+                                        (ctx->algo == GPANN_ALGO_AUTO && kc >= 32 && pts->n * kc >= ((size_t) 1 << 24)));
+    if (want_tensor && ctx->algo == GPANN_ALGO_AUTO && !kmeans_tensor_fits(ctx, (((int) pts->d + 31) / 32) * 32, kc)) want_tensor = false;
     if (want_tensor && !pts->km_tried) GP_TRY(build_kmeans_layout(ctx, const_cast<gpann_points*>(pts), st));
-    if (want_tensor && pts->km_ok) return kmeans_assign_tensor(ctx, pts, d_centroids, kc, d_assign, st);
+    if (want_tensor && pts->km_ok) return kmeans_assign_tensor(ctx, pts, d_centroids, kc, d_assign, d_alive, st);
+    if (ctx->algo == GPANN_ALGO_TENSOR && tensor_shape && !pts->km_ok)
+        return fail(ctx, GPANN_E_OOM, "kmeans tensor path: the split-precision layout could not be built");
     ctx->last_algo = "kmeans_cuda_core";
     AssignParams p;
     p.pts = rows_view(pts);
@@ -984,6 +953,7 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
     p.cchunk = (int) std::max<size_t>(1, std::min<size_t>(kc, (budget - tile_bytes) / per_c));
     p.out_assign = d_assign;
     p.out_mindist = d_mindist;
+    p.alive = d_alive;
     const size_t smem = tile_bytes + (size_t) p.cchunk * per_c;
     const size_t ntiles = (pts->n + kStreamTile - 1) / kStreamTile;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
@@ -1036,12 +1006,12 @@ int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* 
     return check_launch(ctx, "cluster_finalize_kernel");
 }
 
-}  // namespace
+}  // namespace gpimpl
 
-// ---- C ABI -------------------------------------------------------------------------------------------------
-extern "C" {
+// ---- single-device implementations of the C ABI (abi.cu dispatches: plain ctx -> sd_*, group ctx -> multi.cu) ----------
+namespace gpimpl {
 
-int gpann_init(gpann_ctx** out, int device) {
+int sd_init(gpann_ctx** out, int device) {
     if (!out) return GPANN_E_ARG;
     *out = nullptr;
     int count = 0;
@@ -1059,7 +1029,8 @@ int gpann_init(gpann_ctx** out, int device) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return GPANN_E_CUDA;
     }
@@ -1088,14 +1059,17 @@ int gpann_init(gpann_ctx** out, int device) {
     return 0;
 }
 
-void gpann_destroy(gpann_ctx* ctx) {
+void sd_destroy(gpann_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();  // asynchronous entry points may still be running on caller streams
+    comm_destroy(ctx);
     DevBuf* bufs[] = { &ctx->pace, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
-                       &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info };
+                       &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info,
+                       &ctx->gather_send, &ctx->gather_recv, &ctx->km_run_cent, &ctx->km_run_sums, &ctx->km_run_counts,
+                       &ctx->km_run_alive, &ctx->km_run_remap, &ctx->km_run_norms };
     for (DevBuf* b : bufs) release(*b);
     DevBuf* sbufs[] = { &ctx->st_raw[0], &ctx->st_raw[1], &ctx->st_rows, &ctx->st_norms, &ctx->st_ids, &ctx->st_a, &ctx->st_b,
                         &ctx->st_c, &ctx->st_d, &ctx->st_tmp, &ctx->st_narrow };
@@ -1108,31 +1082,32 @@ void gpann_destroy(gpann_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     delete ctx;
 }
 
-const char* gpann_last_error(const gpann_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-int gpann_device(const gpann_ctx* ctx) { return ctx ? ctx->device : -1; }
-int gpann_set_algo(gpann_ctx* ctx, int algo) {
+const char* sd_last_error(const gpann_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int sd_device(const gpann_ctx* ctx) { return ctx ? ctx->device : -1; }
+int sd_set_algo(gpann_ctx* ctx, int algo) {
     if (!ctx || algo < GPANN_ALGO_AUTO || algo > GPANN_ALGO_TENSOR) return GPANN_E_ARG;
     ctx->algo = algo;
     return 0;
 }
-uint64_t gpann_launch_count(const gpann_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int gpann_set_timing(gpann_ctx* ctx, int on) {
+uint64_t sd_launch_count(const gpann_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sd_set_timing(gpann_ctx* ctx, int on) {
     if (!ctx) return GPANN_E_ARG;
     ctx->timing = on ? 1 : 0;
     ctx->timed = false;
     return 0;
 }
-float gpann_last_kernel_ms(gpann_ctx* ctx) {
+float sd_last_kernel_ms(gpann_ctx* ctx) {
     if (!ctx || !ctx->timed) return -1.f;
     float ms = -1.f;
     if (cudaEventSynchronize(ctx->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
     return ms;
 }
-const char* gpann_last_algo(const gpann_ctx* ctx) { return ctx ? ctx->last_algo : "none"; }
-uint64_t gpann_last_ambiguous(gpann_ctx* ctx) {
+const char* sd_last_algo(const gpann_ctx* ctx) { return ctx ? ctx->last_algo : "none"; }
+uint64_t sd_last_ambiguous(gpann_ctx* ctx) {
     if (!ctx || !ctx->km_scal.p) return 0;
     uint32_t v = 0;
     cudaSetDevice(ctx->device);
@@ -1145,7 +1120,7 @@ static int finish_points(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st, gpa
     if (pts->storage != GPANN_STORAGE_F32) {
         int r = build_tensor_bytes(ctx, pts, st);
         if (r != 0) {
-            gpann_points_free(pts);
+            sd_points_free(pts);
             return r;
         }
     }
@@ -1153,7 +1128,7 @@ static int finish_points(gpann_ctx* ctx, gpann_points* pts, cudaStream_t st, gpa
     return 0;
 }
 
-int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base,
+int sd_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base,
                         gpann_points** out) {
     if (!ctx) return GPANN_E_ARG;
     if (!out || (!host_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_upload: bad argument");
@@ -1162,20 +1137,15 @@ int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     *out = nullptr;
     cudaStream_t st = ctx->stream;
-    float* d_f32 = nullptr;
-    CU_TRY(ctx, cudaMalloc(&d_f32, std::max<size_t>(n * d * 4, 256)));
-    if (n) {
-        cudaError_t e = cudaMemcpyAsync(d_f32, host_rows, n * d * 4, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) {
-            cudaFree(d_f32);
-            return fail(ctx, GPANN_E_CUDA, std::string("points_upload H2D: ") + cudaGetErrorString(e));
-        }
-    }
+    OrderScope order(ctx, st);
+    ScopedDev f32;  // freed on every error path; ownership moves to the handle for F32 storage
+    CU_TRY(ctx, f32.alloc(n * d * 4));
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(f32.p, host_rows, n * d * 4, cudaMemcpyHostToDevice, st));
     if (storage == GPANN_STORAGE_AUTO && n) {
         int flags_h[2] = { 1, 1 };
         GP_TRY(reserve(ctx, ctx->flags, 64));
         CU_TRY(ctx, cudaMemcpyAsync(ctx->flags.p, flags_h, 8, cudaMemcpyHostToDevice, st));
-        launch_detect_bytes(d_f32, n * d, (int*) ctx->flags.p, blocks_for(ctx, n * d), st);
+        launch_detect_bytes(f32.as<float>(), n * d, (int*) ctx->flags.p, blocks_for(ctx, n * d), st);
         GP_TRY(check_launch(ctx, "detect_bytes_kernel"));
         CU_TRY(ctx, cudaMemcpyAsync(flags_h, ctx->flags.p, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -1184,40 +1154,37 @@ int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t
         storage = GPANN_STORAGE_F32;
     }
     gpann_points* pts = new (std::nothrow) gpann_points();
-    if (!pts) {
-        cudaFree(d_f32);
-        return fail(ctx, GPANN_E_OOM, "points_upload: host allocation failed");
-    }
+    if (!pts) return fail(ctx, GPANN_E_OOM, "points_upload: host allocation failed");
     pts->ctx = ctx;
     pts->n = n;
     pts->d = d;
     pts->storage = storage;
     pts->id_base = id_base;
     if (storage == GPANN_STORAGE_F32) {
-        pts->rows = d_f32;
+        pts->rows = f32.release();
         pts->pitch = d * 4;
     } else {
         unsigned char* bytes = nullptr;
-        cudaError_t e = cudaMalloc(&bytes, std::max<size_t>(n * d, 256));
-        if (e != cudaSuccess) {
-            cudaFree(d_f32);
+        if (cudaMalloc(&bytes, std::max<size_t>(n * d, 256)) != cudaSuccess) {
+            cudaGetLastError();
             delete pts;
             return fail(ctx, GPANN_E_OOM, "points_upload: out of device memory");
         }
-        if (n) {
-            launch_narrow_rows(d_f32, n, (int) d, (int) d, bytes, blocks_for(ctx, n * d), st);
-            ctx->launches++;
-        }
-        cudaStreamSynchronize(st);
-        cudaFree(d_f32);
         pts->rows = bytes;
         pts->pitch = d;
+        if (n) {
+            launch_narrow_rows(f32.as<float>(), n, (int) d, (int) d, bytes, blocks_for(ctx, n * d), st);
+            ctx->launches++;
+        }
     }
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        sd_points_free(pts);
+        return fail(ctx, GPANN_E_CUDA, std::string("points_upload: ") + cudaGetErrorString(cudaGetLastError()));
+    }
     return finish_points(ctx, pts, st, out);
 }
 
-int gpann_points_upload_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+int sd_points_upload_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
                               gpann_points** out) {
     if (!ctx) return GPANN_E_ARG;
     if (!out || (!host_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_upload_bytes: bad argument");
@@ -1249,7 +1216,7 @@ int gpann_points_upload_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, s
     return finish_points(ctx, pts, ctx->stream, out);
 }
 
-int gpann_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, size_t d, int storage, uint32_t id_base, void* stream,
+int sd_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, size_t d, int storage, uint32_t id_base, void* stream,
                              gpann_points** out) {
     if (!ctx) return GPANN_E_ARG;
     if (!out || (!dev_rows && n) || d == 0 || d > 4096) return fail(ctx, GPANN_E_ARG, "points_from_device: bad argument");
@@ -1270,7 +1237,7 @@ int gpann_points_from_device(gpann_ctx* ctx, const void* dev_rows, size_t n, siz
     return finish_points(ctx, pts, (cudaStream_t) stream, out);
 }
 
-void gpann_points_free(gpann_points* pts) {
+void sd_points_free(gpann_points* pts) {
     if (!pts) return;
     if (pts->ctx) cudaSetDevice(pts->ctx->device);
     if (pts->owns_rows && pts->rows) cudaFree(pts->rows);
@@ -1281,32 +1248,32 @@ void gpann_points_free(gpann_points* pts) {
     if (pts->km_xnorm) cudaFree(pts->km_xnorm);
     delete pts;
 }
-size_t gpann_points_n(const gpann_points* pts) { return pts ? pts->n : 0; }
-size_t gpann_points_d(const gpann_points* pts) { return pts ? pts->d : 0; }
-int gpann_points_storage(const gpann_points* pts) { return pts ? pts->storage : 0; }
+size_t sd_points_n(const gpann_points* pts) { return pts ? pts->n : 0; }
+size_t sd_points_d(const gpann_points* pts) { return pts ? pts->d : 0; }
+int sd_points_storage(const gpann_points* pts) { return pts ? pts->storage : 0; }
 
-int gpann_topk(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric, float* out_dist,
+int sd_topk(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric, float* out_dist,
                uint32_t* out_id, uint32_t* out_count) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts) return fail(ctx, GPANN_E_ARG, "topk: null point set");
     return topk_host(ctx, pts, 0, pts->n, queries, nq, k, metric, out_dist, out_id, out_count, nullptr);
 }
 
-int gpann_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
+int sd_kth_distance(gpann_ctx* ctx, const gpann_points* pts, const float* queries, size_t nq, int k, int metric,
                        float* out_kth) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !out_kth) return fail(ctx, GPANN_E_ARG, "kth_distance: null argument");
     return topk_host(ctx, pts, 0, pts->n, queries, nq, k, metric, nullptr, nullptr, nullptr, out_kth);
 }
 
-int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries, size_t nq,
+int sd_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries, size_t nq,
                      int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts) return fail(ctx, GPANN_E_ARG, "topk_range: null point set");
     return topk_host(ctx, pts, row_begin, row_end, queries, nq, k, metric, out_dist, out_id, out_count, nullptr);
 }
 
-int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+int sd_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
                             const float* queries, size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id,
                             uint32_t* out_count) {
     if (!ctx) return GPANN_E_ARG;
@@ -1314,7 +1281,7 @@ int gpann_topk_stream_bytes(gpann_ctx* ctx, const void* host_rows, size_t n, siz
                                 out_id, out_count, nullptr);
 }
 
-int gpann_topk_stream(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base, const float* queries,
+int sd_topk_stream(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base, const float* queries,
                       size_t nq, int k, size_t chunk_rows, float* out_dist, uint32_t* out_id, uint32_t* out_count, float* out_kth) {
     if (!ctx) return GPANN_E_ARG;
     if (storage < GPANN_STORAGE_AUTO || storage > GPANN_STORAGE_S8) return fail(ctx, GPANN_E_ARG, "topk_stream: bad storage");
@@ -1322,30 +1289,31 @@ int gpann_topk_stream(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d
                                 out_count, out_kth);
 }
 
-int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
-                                   const float* dev_queries, size_t nq, int k, size_t chunk_rows, uint64_t* dev_out_keys,
-                                   void* stream) {
+int sd_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t n, size_t d, int is_signed, uint32_t id_base,
+                                const float* dev_queries, size_t nq, int k, size_t chunk_rows, uint64_t* dev_out_keys, void* stream) {
     if (!ctx) return GPANN_E_ARG;
     if ((!host_rows && n) || !dev_queries || !dev_out_keys) return fail(ctx, GPANN_E_ARG, "topk_stream_bytes_device: null argument");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    OrderScope order(ctx, (cudaStream_t) stream);
     TopkOut o;
     o.keys = dev_out_keys;
     return topk_stream_host(ctx, host_rows, is_signed ? kHostS8 : kHostU8, 0, n, d, id_base, dev_queries, nq, k, chunk_rows, o,
                             (cudaStream_t) stream);
 }
 
-int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
-                      uint64_t* dev_out_keys, void* stream) {
+int sd_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
+                   uint64_t* dev_out_keys, void* stream) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !dev_queries || !dev_out_keys) return fail(ctx, GPANN_E_ARG, "topk_device: null argument");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    OrderScope order(ctx, (cudaStream_t) stream);
     TopkOut o;
     o.keys = dev_out_keys;
-    return topk_dispatch(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, (cudaStream_t) stream);
+    return topk_dispatch(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, (cudaStream_t) stream, nullptr);
 }
 
-int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist,
-                            uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream) {
+int sd_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist,
+                         uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream) {
     if (!ctx) return GPANN_E_ARG;
     if (!dev_keys || parts == 0 || k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "merge_keys: bad argument");
     if (nq == 0) return 0;
@@ -1354,22 +1322,56 @@ int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t par
     o.dist = dev_out_dist;
     o.id = dev_out_id;
     o.keys = dev_out_keys;
-    return launch_merge(ctx, dev_keys, parts, nq, nq, k, o, 0, (cudaStream_t) stream);
+    return launch_merge(ctx, dev_keys, parts, nq, nq, k, o, 0, (cudaStream_t) stream, nullptr, 0);  // no ctx scratch involved
 }
 
-uint64_t gpann_pack_key(float dist, uint32_t id) { return pack_key(dist, id); }
-void gpann_unpack_key(uint64_t key, float* dist, uint32_t* id) {
-    if (dist) *dist = key_dist(key);
-    if (id) *id = key_id(key);
+// The per-rank step of the sharded top-k (north_star: "each GPU computes a local top-k over its shard, and the final
+// merge is an NCCL all-gather of (distance, id) candidates"): local scan of rows [row_begin,row_end) with the per-query
+// bounds all-reduced (min) across the ranks between the sample passes and the main pass, one all-gather of the [nq,k] key
+// blocks, merge.  Every rank ends up with the same result in `out`.  Without a communicator it is the plain local scan.
+// Queries are served in batches no larger than the smallest tensor-path batch, so every rank issues one bound exchange
+// per batch whatever its shard's storage or size.
+int topk_sharded(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
+                 int metric, const TopkOut& out, cudaStream_t st) {
+    if (ctx->comm_size <= 1) return topk_dispatch(ctx, pts, row_begin, row_end, dq, nq, k, metric, out, st, nullptr);
+    if (k < 1 || k > 512) return fail(ctx, GPANN_E_ARG, "topk: k must be in [1,512]");
+    if (nq == 0) return 0;
+    const size_t part = nq * (size_t) k;
+    GP_TRY(reserve(ctx, ctx->gather_send, part * 8));
+    GP_TRY(reserve(ctx, ctx->gather_recv, part * 8 * ctx->comm_size));
+    const BetweenFn between = [ctx](uint32_t* bound, size_t count, cudaStream_t s) { return comm_allreduce_min_u32(ctx, bound, count, s); };
+    const size_t batch = tc_batch_max(ctx, 2);
+    for (size_t q0 = 0; q0 < nq; q0 += batch) {
+        TopkOut local;
+        local.keys = (uint64_t*) ctx->gather_send.p + q0 * k;
+        GP_TRY(topk_dispatch(ctx, pts, row_begin, row_end, dq + q0 * pts->d, std::min(batch, nq - q0), k, metric, local, st, between));
+    }
+    GP_TRY(comm_allgather_u64(ctx, (const uint64_t*) ctx->gather_send.p, (uint64_t*) ctx->gather_recv.p, part, st));
+    return launch_merge(ctx, (const uint64_t*) ctx->gather_recv.p, ctx->comm_size, nq, nq, k, out, 0, st, nullptr, 0);
 }
 
-int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int metric,
-                        int32_t* out_assign, float* out_mindist) {
+int sd_topk_sharded_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
+                           float* dev_out_dist, uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !dev_queries) return fail(ctx, GPANN_E_ARG, "topk_sharded_device: null argument");
+    if (pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "topk: point set does not belong to this context");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    OrderScope order(ctx, (cudaStream_t) stream);
+    TopkOut o;
+    o.dist = dev_out_dist;
+    o.id = dev_out_id;
+    o.keys = dev_out_keys;
+    return topk_sharded(ctx, pts, 0, pts->n, dev_queries, nq, k, metric, o, (cudaStream_t) stream);
+}
+
+int sd_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int metric, int32_t* out_assign,
+                     float* out_mindist) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !centroids || !out_assign) return fail(ctx, GPANN_E_ARG, "kmeans_assign: null argument");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");  // src/kmeans.cpp:229-231
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    OrderScope order(ctx, st);
     const size_t n = pts->n, d = pts->d;
     GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
     GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
@@ -1377,7 +1379,7 @@ int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* ce
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
     if (n) {
         GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p,
-                                    out_mindist ? (float*) ctx->dist_out.p : nullptr, st));
+                                    out_mindist ? (float*) ctx->dist_out.p : nullptr, nullptr, st));
         CU_TRY(ctx, cudaMemcpyAsync(out_assign, ctx->assign.p, n * 4, cudaMemcpyDeviceToHost, st));
         if (out_mindist) CU_TRY(ctx, cudaMemcpyAsync(out_mindist, ctx->dist_out.p, n * 4, cudaMemcpyDeviceToHost, st));
     }
@@ -1385,36 +1387,44 @@ int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* ce
     return 0;
 }
 
-int gpann_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc, int metric,
-                                int32_t* dev_out_assign, float* dev_out_sums, uint64_t* dev_out_counts, void* stream) {
+// assignment + this shard's per-cluster coordinate sums and counts (no division)
+int kmeans_partial(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric, int32_t* d_assign,
+                   const unsigned char* d_alive, float* d_sums, uint64_t* d_counts, cudaStream_t st) {
+    if (pts->n == 0) {
+        CU_TRY(ctx, cudaMemsetAsync(d_sums, 0, kc * pts->d * 4, st));
+        CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, kc * 8, st));
+        return 0;
+    }
+    GP_TRY(kmeans_assign_device(ctx, pts, d_centroids, kc, metric, d_assign, nullptr, d_alive, st));
+    return cluster_sums_device(ctx, pts, d_assign, kc, 0, d_sums, d_counts, st);
+}
+
+int sd_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc, int metric,
+                             int32_t* dev_out_assign, float* dev_out_sums, uint64_t* dev_out_counts, void* stream) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !dev_centroids || !dev_out_sums || !dev_out_counts) return fail(ctx, GPANN_E_ARG, "kmeans_partial: null argument");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
     if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t) stream;
+    OrderScope order(ctx, st);
     int32_t* d_assign = dev_out_assign;
     if (!d_assign) {
         GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(pts->n, 1) * 4));
         d_assign = (int32_t*) ctx->assign.p;
     }
-    if (pts->n == 0) {
-        CU_TRY(ctx, cudaMemsetAsync(dev_out_sums, 0, kc * pts->d * 4, st));
-        CU_TRY(ctx, cudaMemsetAsync(dev_out_counts, 0, kc * 8, st));
-        return 0;
-    }
-    GP_TRY(kmeans_assign_device(ctx, pts, dev_centroids, kc, metric, d_assign, nullptr, st));
-    return cluster_sums_device(ctx, pts, d_assign, kc, 0, dev_out_sums, dev_out_counts, st);
+    return kmeans_partial(ctx, pts, dev_centroids, kc, metric, d_assign, nullptr, dev_out_sums, dev_out_counts, st);
 }
 
-int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int metric, int32_t* out_assign,
-                      uint64_t* out_sizes) {
+int sd_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int metric, int32_t* out_assign,
+                   uint64_t* out_sizes) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !centroids_inout || !out_sizes) return fail(ctx, GPANN_E_ARG, "kmeans_step: null argument");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
     if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    OrderScope order(ctx, st);
     const size_t n = pts->n, d = pts->d;
     GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
     GP_TRY(reserve(ctx, ctx->sums, kc * d * 4));
@@ -1422,7 +1432,7 @@ int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_
     GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids_inout, kc * d * 4, cudaMemcpyHostToDevice, st));
     if (n) {
-        GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p, nullptr, st));
+        GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p, nullptr, nullptr, st));
         GP_TRY(cluster_sums_device(ctx, pts, (const int32_t*) ctx->assign.p, kc, 1, (float*) ctx->sums.p, (uint64_t*) ctx->counts.p, st));
     } else {
         CU_TRY(ctx, cudaMemsetAsync(ctx->sums.p, 0, kc * d * 4, st));
@@ -1435,21 +1445,123 @@ int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_
     return 0;
 }
 
-int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric,
-                    double* out) {
-    if (!ctx) return GPANN_E_ARG;
-    if (!pts || !centroids || !assign || !out) return fail(ctx, GPANN_E_ARG, "objective: null argument");
+// ---- KMeans (src/kmeans.cpp:228-244) with the centroids resident on the device for all rounds ----------------------------
+// Per round: nearest centroid (removed clusters skipped), deterministic per-cluster sums, an all-reduce(sum) of sums and
+// counts when the ctx is a rank of a communicator, division, removal of clusters that lost every member
+// (in place: alive[c] = 0).  d_cent [kc,d] and d_alive [kc] are updated in place; d_counts [kc] holds the last round's
+// (global) cluster sizes; d_assign [n_local] the last round's assignment in ORIGINAL cluster numbers.
+int kmeans_rounds_device(gpann_ctx* ctx, const gpann_points* pts, float* d_cent, size_t kc, int rounds, int metric, int32_t* d_assign,
+                         unsigned char* d_alive, uint64_t* d_counts, cudaStream_t st) {
+    const size_t d = pts->d;
+    GP_TRY(reserve(ctx, ctx->km_run_sums, kc * d * 4));
+    float* d_sums = (float*) ctx->km_run_sums.p;
+    for (int r = 0; r < rounds; ++r) {
+        GP_TRY(kmeans_partial(ctx, pts, d_cent, kc, metric, d_assign, d_alive, d_sums, d_counts, st));
+        if (ctx->comm_size > 1) GP_TRY(comm_allreduce_kmeans(ctx, d_sums, kc * d, d_counts, kc, st));
+        launch_kmeans_update(d_cent, d_sums, d_counts, d_alive, (int) kc, (int) d, st);
+        GP_TRY(check_launch(ctx, "kmeans_update_kernel"));
+    }
+    return 0;
+}
+
+// Final renumbering (RemoveEmptyClusters, src/kmeans.cpp:29-50, applied once): survivors compacted to the front of d_cent /
+// d_counts, assignments renumbered, the number of survivors in d_kc_out.
+int kmeans_compact_device(gpann_ctx* ctx, float* d_cent, size_t kc, size_t d, int32_t* d_assign, size_t n, const unsigned char* d_alive,
+                          uint64_t* d_counts, int* d_kc_out, cudaStream_t st) {
+    GP_TRY(reserve(ctx, ctx->km_run_remap, kc * 4));
+    GP_TRY(reserve(ctx, ctx->km_run_sums, kc * d * 4));
+    launch_kmeans_compact(d_cent, d_counts, d_alive, (int) kc, (int) d, (int32_t*) ctx->km_run_remap.p, d_kc_out, (float*) ctx->km_run_sums.p, st);
+    GP_TRY(check_launch(ctx, "kmeans_compact_kernel"));
+    if (n && d_assign) {
+        launch_remap_assign(d_assign, n, (const int32_t*) ctx->km_run_remap.p, (int) kc, blocks_for(ctx, n), st);
+        GP_TRY(check_launch(ctx, "remap_assign_kernel"));
+    }
+    return 0;
+}
+
+// Queue the whole KMeans call on ctx->stream: H2D of the centroids, `rounds` Lloyd rounds, compaction.  Results stay on the
+// device (ctx->km_run_cent / km_run_counts / assign, survivors in km_run_remap-adjacent scalar); kmeans_run_fetch copies
+// them out.  Split in two so that a group ctx (multi.cu) can queue every rank before any rank waits.
+int kmeans_run_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int rounds, int metric) {
+    if (!pts || !centroids) return fail(ctx, GPANN_E_ARG, "kmeans_run: null argument");
+    if (pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "kmeans_run: point set does not belong to this context");
+    if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");  // src/kmeans.cpp:229-231
+    if (rounds < 0) return fail(ctx, GPANN_E_ARG, "kmeans_run: rounds < 0");
+    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = pts->n, d = pts->d;
-    if (n == 0) {
-        *out = 0.0;
-        return 0;
+    GP_TRY(reserve(ctx, ctx->km_run_cent, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->km_run_counts, kc * 8 + 64));
+    GP_TRY(reserve(ctx, ctx->km_run_alive, kc));
+    GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->km_run_cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->km_run_alive.p, 1, kc, st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->km_run_counts.p, 0, kc * 8 + 64, st));
+    if (n) CU_TRY(ctx, cudaMemsetAsync(ctx->assign.p, 0xFF, n * 4, st));  // -1: the reference's initial closest_center
+    uint64_t* d_counts = (uint64_t*) ctx->km_run_counts.p;
+    int* d_kc_out = (int*) (d_counts + kc);
+    GP_TRY(kmeans_rounds_device(ctx, pts, (float*) ctx->km_run_cent.p, kc, rounds, metric, (int32_t*) ctx->assign.p,
+                                (unsigned char*) ctx->km_run_alive.p, d_counts, st));
+    return kmeans_compact_device(ctx, (float*) ctx->km_run_cent.p, kc, d, (int32_t*) ctx->assign.p, n, (const unsigned char*) ctx->km_run_alive.p,
+                                 d_counts, d_kc_out, st);
+}
+
+int kmeans_run_fetch(gpann_ctx* ctx, const gpann_points* pts, float* centroids_out, size_t kc, int32_t* out_assign, uint64_t* out_sizes,
+                     size_t* out_kc) {
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = pts->n, d = pts->d;
+    const uint64_t* d_counts = (const uint64_t*) ctx->km_run_counts.p;
+    int kc_new = 0;
+    if (centroids_out) CU_TRY(ctx, cudaMemcpyAsync(centroids_out, ctx->km_run_cent.p, kc * d * 4, cudaMemcpyDeviceToHost, st));
+    if (out_sizes) CU_TRY(ctx, cudaMemcpyAsync(out_sizes, d_counts, kc * 8, cudaMemcpyDeviceToHost, st));
+    if (out_assign && n) CU_TRY(ctx, cudaMemcpyAsync(out_assign, ctx->assign.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(&kc_new, d_counts + kc, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (out_kc) *out_kc = (size_t) kc_new;
+    return 0;
+}
+
+int sd_kmeans_run(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int rounds, int metric, int32_t* out_assign,
+                  uint64_t* out_sizes, size_t* out_kc) {
+    if (!ctx) return GPANN_E_ARG;
+    OrderScope order(ctx, ctx->stream);
+    GP_TRY(kmeans_run_enqueue(ctx, pts, centroids_inout, kc, rounds, metric));
+    return kmeans_run_fetch(ctx, pts, centroids_inout, kc, out_assign, out_sizes, out_kc);
+}
+
+// Device form: centroids [kc,d], alive [kc] (caller initialises: 1 = live) and counts [kc] live in caller-owned device memory and
+// are updated in place, nothing is renumbered and nothing synchronises -- bench.py and the torch.distributed driver time
+// Lloyd rounds with it.  With a communicator every rank passes its shard and ends up with identical centroids.
+int sd_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_centroids_inout, size_t kc, int rounds, int metric,
+                         int32_t* dev_out_assign, unsigned char* dev_alive_inout, uint64_t* dev_out_counts, void* stream) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !dev_centroids_inout || !dev_alive_inout || !dev_out_counts) return fail(ctx, GPANN_E_ARG, "kmeans_run_device: null argument");
+    if (pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "kmeans_run: point set does not belong to this context");
+    if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
+    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    OrderScope order(ctx, st);
+    int32_t* d_assign = dev_out_assign;
+    if (!d_assign) {
+        GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(pts->n, 1) * 4));
+        d_assign = (int32_t*) ctx->assign.p;
     }
+    return kmeans_rounds_device(ctx, pts, dev_centroids_inout, kc, rounds, metric, d_assign, dev_alive_inout, dev_out_counts, st);
+}
+
+// sum_i pos_distance(P_i, C_assign[i]) of this ctx's rows, queued on ctx->stream; the double lands in *d_out_ptr (device).
+int objective_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric,
+                      double** d_out_ptr) {
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = pts->n, d = pts->d;
     GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
-    GP_TRY(reserve(ctx, ctx->assign, n * 4));
+    GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->assign.p, assign, n * 4, cudaMemcpyHostToDevice, st));
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(ctx->assign.p, assign, n * 4, cudaMemcpyHostToDevice, st));
     ObjectiveParams p;
     p.pts = rows_view(pts);
     p.centroids = (const float*) ctx->cent.p;
@@ -1463,15 +1575,26 @@ int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centro
     const size_t smem = (size_t) kStreamTile * p.spitch;
     if (smem > 200 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "objective: d too large");
     const size_t ntiles = (n + kStreamTile - 1) / kStreamTile;
-    const unsigned grid = (unsigned) std::min<size_t>(ntiles, (size_t) ctx->num_sms * 4);
+    const unsigned grid = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * 4));
     GP_TRY(reserve(ctx, ctx->misc, (size_t) grid * 8 + 64));
     p.block_sums = (double*) ctx->misc.p;
     double* d_out = p.block_sums + grid;
-    launch_objective(p, grid, smem, d_out, st);
+    launch_objective(p, grid, smem, d_out, st);  // n == 0: every CTA contributes 0
     GP_TRY(check_launch(ctx, "objective_kernel", 2));
-    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaStreamSynchronize(st));
+    *d_out_ptr = d_out;
     return 0;
 }
 
-}  // extern "C"
+int sd_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric,
+                 double* out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (!pts || !centroids || !out || (!assign && pts->n)) return fail(ctx, GPANN_E_ARG, "objective: null argument");
+    OrderScope order(ctx, ctx->stream);
+    double* d_out = nullptr;
+    GP_TRY(objective_enqueue(ctx, pts, centroids, kc, assign, metric, &d_out));
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace gpimpl

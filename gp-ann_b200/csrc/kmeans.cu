@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kStreamTile) kmeans_assign_kernel(const Assign
             __syncthreads();
             if (tid < rows_here) {
                 for (int c = 0; c < nc; ++c) {
+                    if (p.alive && !p.alive[c0 + c]) continue;  // removed cluster
                     const float dist = ref_distance<STORAGE>(myrow, s_c + c * p.qpitch, p.pts.d, p.metric);
                     if (dist < best_dist) {
                         best_dist = dist;
@@ -236,6 +237,53 @@ __global__ void normalize_centroids_kernel(float* sums, const uint64_t* counts, 
     for (int j = threadIdx.x; j < d; j += blockDim.x) sums[(size_t) c * d + j] = sums[(size_t) c * d + j] / (float) counts[c];
 }
 
+// ---- gpann_kmeans_run: Lloyd rounds without a host round trip --------------------------------------------------------
+// centroids[c] = sums[c] / counts[c] (NormalizeCentroidsL2, src/kmeans.cpp:104-114); a cluster without members is REMOVED
+// as RemoveEmptyClusters does (src/kmeans.cpp:29-50), but in place: alive[c] = 0 and its row zeroed.  Later rounds skip it,
+// which selects the same winner as the reference's renumbered scan (compaction keeps the order of the survivors, so
+// "lowest index wins ties" is unchanged); kmeans_compact_kernel renumbers once, at the end.
+__global__ void kmeans_update_kernel(float* centroids, const float* sums, const uint64_t* counts, unsigned char* alive, int kc, int d) {
+    const int c = blockIdx.x;
+    const uint64_t cnt = counts[c];
+    const bool live = alive[c] != 0 && cnt != 0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x)
+        centroids[(size_t) c * d + j] = live ? sums[(size_t) c * d + j] / (float) cnt : 0.f;
+    if (threadIdx.x == 0 && !live) alive[c] = 0;
+}
+
+// remap[c] = new index of a surviving cluster (-1 for removed ones), *kc_out = survivors; centroid rows and counts are
+// compacted to the front (through cent_tmp [kc,d]).  One CTA.
+__global__ void kmeans_compact_kernel(float* centroids, uint64_t* counts, const unsigned char* alive, int kc, int d, int32_t* remap,
+                                      int* kc_out, float* cent_tmp) {
+    __shared__ int s_total;
+    if (threadIdx.x == 0) {
+        int l = 0;
+        for (int c = 0; c < kc; ++c) remap[c] = alive[c] ? l++ : -1;
+        s_total = l;
+        *kc_out = l;
+    }
+    __syncthreads();
+    if (s_total == kc) return;
+    for (size_t i = threadIdx.x; i < (size_t) kc * d; i += blockDim.x) cent_tmp[i] = centroids[i];
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < (size_t) kc * d; i += blockDim.x) {
+        const int c = (int) (i / d), j = (int) (i - (size_t) c * d);
+        if (remap[c] >= 0) centroids[(size_t) remap[c] * d + j] = cent_tmp[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < kc; ++c)
+            if (remap[c] >= 0) counts[remap[c]] = counts[c];  // remap[c] <= c: in-place forward copy is safe
+    }
+}
+
+__global__ void remap_assign_kernel(int32_t* assign, size_t n, const int32_t* remap, int kc) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int a = assign[i];
+        if (a >= 0 && a < kc) assign[i] = remap[a];
+    }
+}
+
 // sum_i pos_distance(P_i, C_{a_i}) with every f32 term widened to double (src/kmeans.cpp:246-249); fixed-order
 // two-level reduction (per-CTA partials, summed in CTA order by objective_final_kernel).
 template <int STORAGE>
@@ -321,6 +369,16 @@ void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaSt
 void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d, int normalize,
                              float* out, cudaStream_t st) {
     cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(seg_sums, seg_begin, counts, kc, d, normalize, out);
+}
+void launch_kmeans_update(float* centroids, const float* sums, const uint64_t* counts, unsigned char* alive, int kc, int d, cudaStream_t st) {
+    kmeans_update_kernel<<<(unsigned) kc, 128, 0, st>>>(centroids, sums, counts, alive, kc, d);
+}
+void launch_kmeans_compact(float* centroids, uint64_t* counts, const unsigned char* alive, int kc, int d, int32_t* remap, int* kc_out,
+                           float* cent_tmp, cudaStream_t st) {
+    kmeans_compact_kernel<<<1, 1024, 0, st>>>(centroids, counts, alive, kc, d, remap, kc_out, cent_tmp);
+}
+void launch_remap_assign(int32_t* assign, size_t n, const int32_t* remap, int kc, int blocks, cudaStream_t st) {
+    remap_assign_kernel<<<blocks, 256, 0, st>>>(assign, n, remap, kc);
 }
 void launch_objective(const ObjectiveParams& p, unsigned grid, size_t smem, double* d_out, cudaStream_t st) {
     if (p.pts.storage == kF32) objective_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);

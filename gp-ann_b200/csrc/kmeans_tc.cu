@@ -76,11 +76,12 @@ __global__ void split_rows_bf16_kernel(const float* rows, size_t n, int d, int d
 
 // offset >= max |dot~| + max hn, so that score = dot~ - hn + offset >= 0 for every (point, centroid); hn'[j] = hn[j] -
 // offset for real centroids and 0 for padding ones (their accumulators are exactly 0 -> score +0, the minimum).
+// Removed centroids (alive[j] == 0: all-zero rows, see kmeans_update_kernel) are treated like padding.
 __global__ void kmeans_centroid_consts_kernel(const float* xmax, const float* cmax, const float* hnmax, float* hn, int kc, int kc_pad,
-                                              Consts* consts) {
+                                              const unsigned char* alive, Consts* consts) {
     const float xm = *xmax, cm = *cmax;
     const float offset = 1.02f * xm * cm + *hnmax + 1e-30f;
-    for (int j = threadIdx.x; j < kc_pad; j += blockDim.x) hn[j] = j < kc ? hn[j] - offset : 0.f;
+    for (int j = threadIdx.x; j < kc_pad; j += blockDim.x) hn[j] = (j < kc && (!alive || alive[j])) ? hn[j] - offset : 0.f;
     if (threadIdx.x == 0) {
         consts->offset = offset;
         consts->cmax = cm;
@@ -374,12 +375,14 @@ __global__ void kmeans_finalize_kernel(const KmFinalizeParams p) {
         const float slack = 2.f * err + gamma_ref * dist1;
         const float thr = s1 - slack;
         uint32_t mode;
-        if (m.j[0] >= p.kc) {
+        const bool bad0 = m.j[0] >= p.kc || (p.alive && !p.alive[m.j[0]]);  // padding or removed centroid
+        const bool bad1 = m.j[1] >= p.kc || (p.alive && !p.alive[m.j[1]]);
+        if (bad0) {
             mode = kModeFull;
         } else if (s2 < thr) {
             p.out_assign[i] = m.j[0];
             continue;
-        } else if (s3 >= thr || m.j[1] >= p.kc) {
+        } else if (s3 >= thr || bad1) {
             mode = kModeFull;
         } else if ((m.j[0] >> 5) == (m.j[1] >> 5)) {
             mode = kModeChunk;
@@ -458,9 +461,10 @@ __global__ void kmeans_resolve_kernel(const KmFinalizeParams p) {
             uint64_t b = kEmptyKey;
             if (pm == kModeChunk) {
                 const int j = (int) (px & ~31u) + lane;
-                if (j < p.kc) b = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
+                if (j < p.kc && (!p.alive || p.alive[j])) b = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
             } else {
                 for (int j = lane; j < p.kc; j += 32) {
+                    if (p.alive && !p.alive[j]) continue;
                     const uint64_t key = pack_key(exact_l2(x, p.centroids + (size_t) j * p.d, p.d), (uint32_t) j);
                     b = key < b ? key : b;
                 }
@@ -485,8 +489,8 @@ void launch_split_rows_bf16(const float* rows, size_t n, int d, int dpad, size_t
     kmtc::split_rows_bf16_kernel<<<blocks, 256, 0, st>>>(rows, n, d, dpad, n_pad, out_rows, out_norm, out_hn, max_norm, max_hn);
 }
 void launch_kmeans_centroid_consts(const float* xmax, const float* cmax, const float* hnmax, float* hn, int kc, int kc_pad,
-                                   kmtc::Consts* consts, cudaStream_t st) {
-    kmtc::kmeans_centroid_consts_kernel<<<1, 256, 0, st>>>(xmax, cmax, hnmax, hn, kc, kc_pad, consts);
+                                   const unsigned char* alive, kmtc::Consts* consts, cudaStream_t st) {
+    kmtc::kmeans_centroid_consts_kernel<<<1, 256, 0, st>>>(xmax, cmax, hnmax, hn, kc, kc_pad, alive, consts);
 }
 void launch_kmeans_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const kmtc::Args& a, unsigned grid, size_t smem,
                       cudaStream_t st) {

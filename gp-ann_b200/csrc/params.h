@@ -28,6 +28,8 @@ struct StreamParams {
     int qpitch;             // shared-memory query pitch in floats (multiple of 4)
     int vec_ok;             // rows can be fetched with 16-byte loads
     uint64_t* partial;      // [gridDim.x, nq, k]
+    const int* gate;        // optional device flag: the kernel runs only when (*gate != 0) == gate_want (asynchronous fall-backs)
+    int gate_want;
 };
 
 struct MergeParams {
@@ -42,6 +44,8 @@ struct MergeParams {
     uint32_t* out_count;
     float* out_kth;
     int kth_full_only;      // bound mode: out_kth = min(out_kth, k-th distance) and only if k valid keys were found
+    const int* gate;        // optional device flag: the kernel runs only when (*gate != 0) == gate_want
+    int gate_want;
 };
 
 // ---- kmeans.cu ----------------------------------------------------------------------------------------------
@@ -61,6 +65,8 @@ struct AssignParams {
     int spitch, qpitch, vec_ok;
     int32_t* out_assign;     // [n]
     float* out_mindist;      // optional [n]
+    const unsigned char* alive;  // optional [kc]: centroids with alive[c] == 0 are skipped (clusters removed by an earlier
+                                 // round of gpann_kmeans_run: RemoveEmptyClusters without renumbering, src/kmeans.cpp:29-50)
 };
 
 struct ReduceParams {
@@ -161,6 +167,7 @@ struct Args {
     uint32_t pace_window;    // tiles a CTA may run ahead of the slowest CTA of its split (kPaceWindow; tests shrink it)
     uint32_t* pace;          // optional [S*G] tile positions of the CTAs (zeroed before the launch): L2 pacing of a split's CTAs
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
+    const int* gate;         // optional device flag (queries are integer-valued): the kernel returns at once when *gate == 0
 };
 
 // Shared-memory footprint (+1 KB so the operand area can be aligned to 1024 bytes).
@@ -239,6 +246,7 @@ struct KmFinalizeParams {
     uint32_t* amb_list;      // [n] ambiguous point rows (mode in the top 2 bits)
     uint32_t* amb_count;
     uint2* amb_info;         // [n] candidates of an ambiguous point: {j1, j2 | mode << 30}
+    const unsigned char* alive;  // optional [kc]: removed centroids (see AssignParams::alive)
 };
 
 // ---- launchers (each defined in the translation unit that owns the kernel) -------------------------------------
@@ -257,6 +265,11 @@ void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaSt
 void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d,
                              int normalize, float* out, cudaStream_t st);
 void launch_objective(const ObjectiveParams& p, unsigned grid, size_t smem, double* d_out, cudaStream_t st);
+// gpann_kmeans_run (device-resident Lloyd rounds): centroid update with removed-cluster tracking, final compaction
+void launch_kmeans_update(float* centroids, const float* sums, const uint64_t* counts, unsigned char* alive, int kc, int d, cudaStream_t st);
+void launch_kmeans_compact(float* centroids, uint64_t* counts, const unsigned char* alive, int kc, int d, int32_t* remap, int* kc_out,
+                           float* cent_tmp, cudaStream_t st);
+void launch_remap_assign(int32_t* assign, size_t n, const int32_t* remap, int kc, int blocks, cudaStream_t st);
 // stable radix sort of (key, value) pairs on the low `bits` bits; tmp == nullptr only queries tmp_bytes
 cudaError_t sort_pairs_u32(void* tmp, size_t& tmp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
                            uint32_t* vals_out, size_t n, int bits, cudaStream_t st);
@@ -264,7 +277,7 @@ cudaError_t sort_pairs_u32(void* tmp, size_t& tmp_bytes, const uint32_t* keys_in
 void launch_detect_bytes(const float* x, size_t count, int* flags, int blocks, cudaStream_t st);
 void launch_narrow_rows(const float* x, size_t n, int d, int pitch, unsigned char* out, int blocks, cudaStream_t st);
 void launch_byte_norms(const unsigned char* rows, size_t n, int d, size_t pitch, int is_signed, uint32_t* norms, uint32_t* index,
-                       int blocks, cudaStream_t st);
+                       int num_sms, cudaStream_t st);
 void launch_gather_sorted_rows(const unsigned char* rows, size_t n, int d, size_t pitch, const uint32_t* perm,
                                const uint32_t* sorted_norms, uint32_t id_base, size_t n_pad, unsigned char* out_rows,
                                int32_t* out_norms, uint32_t* out_ids, int blocks, cudaStream_t st);
@@ -283,7 +296,7 @@ cudaError_t kmtc_set_attributes();
 void launch_split_rows_bf16(const float* rows, size_t n, int d, int dpad, size_t n_pad, unsigned short* out_rows, float* out_norm,
                             float* out_hn, float* max_norm, float* max_hn, int blocks, cudaStream_t st);
 void launch_kmeans_centroid_consts(const float* xmax, const float* cmax, const float* hnmax, float* hn, int kc, int kc_pad,
-                                   kmtc::Consts* consts, cudaStream_t st);
+                                   const unsigned char* alive, kmtc::Consts* consts, cudaStream_t st);
 void launch_kmeans_tc(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const kmtc::Args& a, unsigned grid, size_t smem,
                       cudaStream_t st);
 void launch_kmeans_finalize(const KmFinalizeParams& p, int blocks, cudaStream_t st);

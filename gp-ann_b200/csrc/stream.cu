@@ -20,8 +20,10 @@ namespace gpann {
 template <int STORAGE>
 __global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.gate && ((*reinterpret_cast<const volatile int*>(p.gate) != 0) != (p.gate_want != 0))) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q0 = blockIdx.y * p.qb;
+    // query batches of qb: blockIdx.y strides over them (the host keeps gridDim.y <= 65535)
+    for (int q0 = blockIdx.y * p.qb; q0 < p.nq; q0 += gridDim.y * p.qb) {
     const int nqb = min(p.qb, p.nq - q0);
     const int elem = STORAGE == kF32 ? 4 : 1;
     const int row_bytes = p.d * elem;
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(kStreamTile) topk_stream_kernel(const StreamPa
         uint64_t* dst = p.partial + ((size_t) blockIdx.x * p.nq + (q0 + q)) * p.k;
         warp_select_topk_dyn<32>(b, s_cnt[q], p.k, dst, lane, p.cap);
     }
+    __syncthreads();  // the next query batch reuses the shared-memory buffers
+    }
 }
 
 // Merge `parts` ascending key lists per query into the k smallest.  One warp per query; keys [parts, nq, k].
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t q = (size_t) blockIdx.x * 4 + warp;
     if (q >= p.nq) return;
+    if (p.gate && ((*reinterpret_cast<const volatile int*>(p.gate) != 0) != (p.gate_want != 0))) return;
     uint64_t* win = reinterpret_cast<uint64_t*>(smem_raw) + (size_t) warp * p.cap;  // [cap]
     // running best k in win[0..k), incoming keys appended behind, select when the window is full
     int cnt = 0;

@@ -1,7 +1,10 @@
 // gpann_dropin.h -- glue between the reference-shaped C++ entry points (recall.h, kmeans.h, ClosestLeaders) and
 // the C ABI of libgpann_cuda.so (include/gpann.h).
 //
-// One process-wide gpann_ctx on device $GPANN_DEVICE (default 0), created on first use.  The reference calls
+// One process-wide gpann_ctx, created on first use: a group over the devices listed in $GPANN_DEVICES ("0,1,2,3":
+// gpann_init_multi -- row-sharded point sets, NCCL all-gather / all-reduce inside the library, so ComputeGroundTruth and
+// KMeans keep their single-call signatures at 8 GPUs, src/recall.h:25-39, src/kmeans.cpp:228-244), else the single
+// device $GPANN_DEVICE (default 0).  The reference calls
 // KMeans concurrently from parlay workers (kmeans_tree_router.cpp:22-37, partitioning.cpp:468-476) while a
 // gpann_ctx is externally synchronised, so every batched call holds the context mutex.  Errors become
 // std::runtime_error, the reference's own convention (kmeans.cpp:229-231); there is no CPU fallback.
@@ -11,6 +14,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/gpann.h"
 
@@ -26,8 +30,19 @@ struct Session {
     gpann_ctx* ctx = nullptr;
     std::mutex mutex;
     Session() {
+        std::vector<int> devices;
+        if (const char* list = std::getenv("GPANN_DEVICES")) {
+            for (const char* p = list; *p;) {
+                char* end = nullptr;
+                const long v = std::strtol(p, &end, 10);
+                if (end == p) break;
+                devices.push_back((int) v);
+                p = (*end == ',') ? end + 1 : end;
+            }
+        }
         const char* dev = std::getenv("GPANN_DEVICE");
-        const int rc = gpann_init(&ctx, dev ? std::atoi(dev) : 0);
+        const int rc = devices.size() > 1 ? gpann_init_multi(&ctx, devices.data(), (int) devices.size())
+                                          : gpann_init(&ctx, !devices.empty() ? devices[0] : (dev ? std::atoi(dev) : 0));
         if (rc != 0)
             throw std::runtime_error("gpann: no usable CUDA device (gpann_init returned " + std::to_string(rc) +
                                      "); the GPU hot path has no CPU fallback");

@@ -7,8 +7,9 @@ bench and the torch.distributed multi-GPU driver use.  There is no CPU fallback:
 CUDA device is missing, `Context()` raises.
 """
 from .lib import (ALGO_AUTO, ALGO_STREAM, ALGO_TENSOR, EMPTY_KEY, INVALID_ID, L2, MIPS, STORAGE_AUTO, STORAGE_F32,
-                  STORAGE_S8, STORAGE_U8, Context, GpannError, Points, lib_path, load_library, pack_key, unpack_keys)
-from .api import (closest_leaders, compute_distance_to_kth_neighbor, compute_ground_truth, kmeans, objective_value,
+                  STORAGE_S8, STORAGE_U8, Context, GpannError, Points, comm_unique_id, lib_path, load_library, pack_key,
+                  unpack_keys)
+from .api import (closest_leaders, compute_distance_to_kth_neighbor, compute_ground_truth, kmeans, kmeans_by_steps, objective_value,
                   remove_empty_clusters)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

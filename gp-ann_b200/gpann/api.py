@@ -72,6 +72,22 @@ def kmeans(ctx, points, centroids, rounds=NUM_ROUNDS):
         raise GpannError("KMeans #centroids < 1")  # src/kmeans.cpp:229-231
     pts, own = _as_points(ctx, points)
     try:
+        # one call: the centroids stay on the device for all rounds (gpann_kmeans_run); kmeans_by_steps below is the
+        # round-by-round form with the reference's host-side RemoveEmptyClusters, kept for the parity tests
+        assign, centroids, _ = ctx.kmeans_run(pts, centroids, rounds)
+        return assign, centroids
+    finally:
+        if own:
+            pts.free()
+
+
+def kmeans_by_steps(ctx, points, centroids, rounds=NUM_ROUNDS):
+    """KMeans as the reference structures it: per round one gpann_kmeans_step and the host-side empty-cluster compaction."""
+    centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+    if centroids.shape[0] < 1:
+        raise GpannError("KMeans #centroids < 1")
+    pts, own = _as_points(ctx, points)
+    try:
         assign = np.full(pts.n, -1, np.int32)
         for _ in range(rounds):
             assign, centroids, sizes = ctx.kmeans_step(pts, centroids)

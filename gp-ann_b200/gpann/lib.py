@@ -16,6 +16,12 @@ EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
 _vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
 SYMBOLS = {
     "gpann_init": (_i, [C.POINTER(_vp), _i]),
+    "gpann_init_multi": (_i, [C.POINTER(_vp), C.POINTER(_i), _i]),
+    "gpann_num_devices": (_i, [_vp]),
+    "gpann_comm_unique_id": (_i, [_vp]),
+    "gpann_comm_init_rank": (_i, [_vp, _i, _i, _vp]),
+    "gpann_comm_size": (_i, [_vp]),
+    "gpann_comm_rank": (_i, [_vp]),
     "gpann_destroy": (None, [_vp]),
     "gpann_last_error": (C.c_char_p, [_vp]),
     "gpann_device": (_i, [_vp]),
@@ -35,6 +41,7 @@ SYMBOLS = {
     "gpann_topk": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "gpann_kth_distance": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
     "gpann_topk_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp]),
+    "gpann_topk_sharded_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
     "gpann_topk_stream_bytes": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp]),
     "gpann_topk_stream": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp, _vp]),
     "gpann_topk_stream_bytes_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp]),
@@ -45,6 +52,8 @@ SYMBOLS = {
     "gpann_kmeans_assign": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "gpann_kmeans_step": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp]),
     "gpann_kmeans_partial_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
+    "gpann_kmeans_run": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, C.POINTER(_sz)]),
+    "gpann_kmeans_run_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
     "gpann_objective": (_i, [_vp, _vp, _vp, _sz, _vp, _i, C.POINTER(C.c_double)]),
 }
 
@@ -93,18 +102,46 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (rank 0 creates it, the caller ships it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = load_library().gpann_comm_unique_id(buf)
+    if rc != 0:
+        raise GpannError(f"gpann_comm_unique_id failed with code {rc} (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 class Context:
-    """One gpann_ctx (one CUDA device).  Externally synchronised: one call at a time."""
+    """One gpann_ctx: one CUDA device (`device` an int) or a GROUP over several devices of this process (`device` a
+    list: gpann_init_multi -- point sets are sharded by rows, exchanges are NCCL collectives inside the library).
+    Externally synchronised: one call at a time."""
 
     def __init__(self, device=0):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.gpann_init(C.byref(h), int(device))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(x) for x in device])
+            rc = self.lib.gpann_init_multi(C.byref(h), devs, len(device))
+        else:
+            rc = self.lib.gpann_init(C.byref(h), int(device))
         if rc != 0:
             raise GpannError(f"gpann_init(device={device}) failed with code {rc}: no usable sm_100 CUDA device "
                              "(there is no CPU fallback)")
         self.h = h
         self.device = device
+
+    @property
+    def num_devices(self):
+        return int(self.lib.gpann_num_devices(self.h))
+
+    def comm_init(self, nranks, rank, unique_id):
+        """Join an NCCL communicator of `nranks` single-device contexts (one per process).  Collective."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.gpann_comm_init_rank(self.h, int(nranks), int(rank), buf))
+
+    @property
+    def comm_size(self):
+        return int(self.lib.gpann_comm_size(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -179,8 +216,15 @@ class Context:
         return p
 
     # ---- top-k ----
+    @staticmethod
+    def _rows(a, d, what):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if a.ndim != 2 or a.shape[1] != d:
+            raise GpannError(f"{what}: expected rows of {d} floats, got shape {a.shape}")
+        return a
+
     def topk(self, pts, queries, k, metric=L2, row_range=None, want_dist=True, want_count=True):
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = self._rows(queries, pts.d, "topk queries")
         nq = q.shape[0]
         dist = np.empty((nq, k), np.float32) if want_dist else None
         ids = np.empty((nq, k), np.uint32)
@@ -222,7 +266,7 @@ class Context:
                                                            C.c_void_p(stream or 0)))
 
     def kth_distance(self, pts, queries, k, metric=L2):
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = self._rows(queries, pts.d, "kth_distance queries")
         out = np.empty(q.shape[0], np.float32)
         self.check(self.lib.gpann_kth_distance(self.h, pts.h, _ptr(q), q.shape[0], k, metric, _ptr(out)))
         return out
@@ -238,7 +282,7 @@ class Context:
 
     # ---- k-means ----
     def kmeans_assign(self, pts, centroids, metric=L2, want_mindist=False):
-        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        c = self._rows(centroids, pts.d, "kmeans_assign centroids")
         out = np.empty(pts.n, np.int32)
         md = np.empty(pts.n, np.float32) if want_mindist else None
         self.check(self.lib.gpann_kmeans_assign(self.h, pts.h, _ptr(c), c.shape[0], metric, _ptr(out), _ptr(md)))
@@ -246,11 +290,34 @@ class Context:
 
     def kmeans_step(self, pts, centroids, metric=L2):
         """One Lloyd round.  Returns (assignment, new centroids incl. all-zero rows of empty clusters, sizes)."""
-        c = np.ascontiguousarray(centroids, dtype=np.float32).copy()
+        c = self._rows(centroids, pts.d, "kmeans_step centroids").copy()
         assign = np.empty(pts.n, np.int32)
         sizes = np.empty(c.shape[0], np.uint64)
         self.check(self.lib.gpann_kmeans_step(self.h, pts.h, _ptr(c), c.shape[0], metric, _ptr(assign), _ptr(sizes)))
         return assign, c, sizes
+
+    def kmeans_run(self, pts, centroids, rounds=20, metric=L2, want_assign=True):
+        """KMeans (src/kmeans.cpp:228-244) in one call, centroids resident on the device for all rounds.  Returns
+        (assignment of the last round, renumbered; surviving centroids; their sizes)."""
+        c = self._rows(centroids, pts.d, "kmeans_run centroids").copy()
+        assign = np.empty(pts.n, np.int32) if want_assign else None
+        sizes = np.empty(c.shape[0], np.uint64)
+        kc = C.c_size_t(0)
+        self.check(self.lib.gpann_kmeans_run(self.h, pts.h, _ptr(c), c.shape[0], int(rounds), metric, _ptr(assign), _ptr(sizes),
+                                             C.byref(kc)))
+        return assign, np.ascontiguousarray(c[:kc.value]), sizes[:kc.value]
+
+    def kmeans_run_device(self, pts, dev_centroids, kc, rounds, dev_alive, dev_counts, dev_assign=None, metric=L2, stream=None):
+        self.check(self.lib.gpann_kmeans_run_device(self.h, pts.h, C.c_void_p(dev_centroids), kc, int(rounds), metric,
+                                                    C.c_void_p(dev_assign or 0), C.c_void_p(dev_alive), C.c_void_p(dev_counts),
+                                                    C.c_void_p(stream or 0)))
+
+    def topk_sharded_device(self, pts, dev_queries, nq, k, dev_out_dist=None, dev_out_id=None, dev_out_keys=None, metric=L2,
+                            stream=None):
+        """The sharded step in one call: local scan + bounds all-reduce(min) + key all-gather + merge (collective)."""
+        self.check(self.lib.gpann_topk_sharded_device(self.h, pts.h, C.c_void_p(dev_queries), nq, k, metric,
+                                                      C.c_void_p(dev_out_dist or 0), C.c_void_p(dev_out_id or 0),
+                                                      C.c_void_p(dev_out_keys or 0), C.c_void_p(stream or 0)))
 
     def kmeans_partial_device(self, pts, dev_centroids, kc, dev_sums, dev_counts, dev_assign=None, metric=L2, stream=None):
         self.check(self.lib.gpann_kmeans_partial_device(self.h, pts.h, C.c_void_p(dev_centroids), kc, metric,
@@ -258,8 +325,10 @@ class Context:
                                                         C.c_void_p(dev_counts), C.c_void_p(stream or 0)))
 
     def objective(self, pts, centroids, assign, metric=L2):
-        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        c = self._rows(centroids, pts.d, "objective centroids")
         a = np.ascontiguousarray(assign, dtype=np.int32)
+        if a.shape != (pts.n,):
+            raise GpannError(f"objective: expected {pts.n} assignments, got shape {a.shape}")
         out = C.c_double()
         self.check(self.lib.gpann_objective(self.h, pts.h, _ptr(c), c.shape[0], _ptr(a), metric, C.byref(out)))
         return out.value

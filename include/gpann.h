@@ -8,7 +8,11 @@
  *
  * Conventions
  *  - extern "C", plain pointers and sizes, no exceptions and no STL across the boundary.
- *  - One gpann_ctx per CUDA device; a ctx is externally synchronised (one call at a time).
+ *  - One gpann_ctx per CUDA device (gpann_init), or one GROUP ctx over several devices of this process (gpann_init_multi:
+ *    point sets are sharded by rows, every entry point below that takes host buffers works on it unchanged, the exchanges
+ *    are NCCL collectives inside the library).  A ctx is externally synchronised: one call at a time.  A call that returned
+ *    while its work is still queued (the *_device entry points) keeps owning the ctx's scratch buffers; the next call on
+ *    the same ctx -- on any stream -- is ordered behind it by the library (a stream-wait on an event, no host wait).
  *  - Every function returns 0 on success or a negative GPANN_E_* code; gpann_last_error(ctx) has the text.
  *  - Host entry points borrow caller-owned host buffers for the duration of the call; the library owns all
  *    device memory behind the opaque handles.  The *_device entry points take device pointers and a
@@ -31,7 +35,7 @@ extern "C" {
 typedef struct gpann_ctx gpann_ctx;
 typedef struct gpann_points gpann_points;
 
-enum { GPANN_OK = 0, GPANN_E_CUDA = -1, GPANN_E_ARG = -2, GPANN_E_OOM = -3, GPANN_E_UNSUPPORTED = -4 };
+enum { GPANN_OK = 0, GPANN_E_CUDA = -1, GPANN_E_ARG = -2, GPANN_E_OOM = -3, GPANN_E_UNSUPPORTED = -4, GPANN_E_NCCL = -5 };
 
 /* Distance metric.  The reference selects it at compile time (-DMIPS_DISTANCE, src/dist.cpp:75-81). */
 enum { GPANN_METRIC_L2 = 0, GPANN_METRIC_MIPS = 1 };
@@ -49,6 +53,22 @@ enum { GPANN_ALGO_AUTO = 0, GPANN_ALGO_STREAM = 1, GPANN_ALGO_TENSOR = 2 };
 
 /* ---- context ------------------------------------------------------------------------------------------- */
 int gpann_init(gpann_ctx** out, int device);
+/* One ctx over `ndev` devices of this process (the reference's entry points are single-call,
+ * single-process by signature -- ComputeGroundTruth src/recall.h:25-39, KMeans src/kmeans.cpp:228-244 -- so the shards live
+ * behind one handle): a worker thread, a stream and an NCCL communicator rank (ncclCommInitAll) per device.
+ * gpann_points_upload* shard the rows [r*ceil(n/ndev), ...) with global ids; gpann_topk / gpann_kth_distance /
+ * gpann_topk_range / gpann_topk_stream* / gpann_kmeans_assign / gpann_kmeans_step / gpann_kmeans_run / gpann_objective run
+ * on all devices at once (bounds all-reduce(min) + key all-gather + merge; sums/counts all-reduce per Lloyd round).
+ * The *_device entry points and gpann_points_from_device need a single-device ctx (GPANN_E_UNSUPPORTED on a group). */
+int gpann_init_multi(gpann_ctx** out, const int* devices, int ndev);
+int gpann_num_devices(const gpann_ctx* ctx);
+/* Several PROCESSES, one single-device ctx each (torchrun): rank 0 calls gpann_comm_unique_id (128 bytes), the caller
+ * ships the bytes to the other ranks, every rank calls gpann_comm_init_rank (collective: ncclCommInitRank).  Afterwards
+ * gpann_topk_sharded_device and gpann_kmeans_run_device treat the ctx's point set as ONE SHARD of the whole. */
+int gpann_comm_unique_id(void* out_id128);
+int gpann_comm_init_rank(gpann_ctx* ctx, int nranks, int rank, const void* id128);
+int gpann_comm_size(const gpann_ctx* ctx);
+int gpann_comm_rank(const gpann_ctx* ctx);
 void gpann_destroy(gpann_ctx* ctx);
 const char* gpann_last_error(const gpann_ctx* ctx);
 int gpann_device(const gpann_ctx* ctx);
@@ -119,6 +139,13 @@ int gpann_topk_stream_bytes_device(gpann_ctx* ctx, const void* host_rows, size_t
  * multi-GPU path: every rank runs it on its shard, all-gathers the keys and calls gpann_merge_keys_device. */
 int gpann_topk_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
                       uint64_t* dev_out_keys, void* stream);
+/* The sharded step in one call (north_star: "each GPU computes a local top-k over its shard, and the final merge is an NCCL
+ * all-gather of (distance, id) candidates over NVLink"): local scan of this rank's shard with the per-query bounds
+ * all-reduced (min) across the ranks after the sample passes, all-gather of the [nq,k] key blocks, merge.  Every rank
+ * receives the full result (any of dev_out_dist / dev_out_id / dev_out_keys, [nq,k]).  Asynchronous on `stream`; collective:
+ * all ranks of the communicator call it with the same queries, k and metric.  Without a communicator = gpann_topk_device. */
+int gpann_topk_sharded_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_queries, size_t nq, int k, int metric,
+                              float* dev_out_dist, uint32_t* dev_out_id, uint64_t* dev_out_keys, void* stream);
 /* Range-restricted scan (InvertedIndex buckets, src/inverted_index.h:43-75): only rows in
  * [row_begin,row_end) are scanned; ids are id_base + row. */
 int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries,
@@ -147,6 +174,19 @@ int gpann_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_
 int gpann_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc,
                                 int metric, int32_t* dev_out_assign, float* dev_out_sums, uint64_t* dev_out_counts,
                                 void* stream);
+/* KMeans (src/kmeans.cpp:228-244) as ONE call: `rounds` Lloyd rounds (the reference's NUM_ROUNDS is 20) with the centroids
+ * resident on the device -- no per-round host round trip.  A cluster that loses all members is removed as
+ * RemoveEmptyClusters does (src/kmeans.cpp:29-50); the renumbering is applied once at the end: on return the first *out_kc
+ * rows of centroids_inout are the surviving centroids, out_sizes[0..*out_kc) their sizes and out_assign [n] the LAST round's
+ * assignment (against the pre-update centroids, renumbered) -- exactly what the reference returns.  out_assign / out_sizes
+ * may be NULL.  On a group ctx (or a ctx with a communicator) sums and counts are all-reduced over NCCL every round. */
+int gpann_kmeans_run(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int rounds, int metric,
+                     int32_t* out_assign, uint64_t* out_sizes, size_t* out_kc);
+/* Device form (asynchronous on `stream`, nothing renumbered): centroids [kc,d], alive [kc] (1 = live; the caller sets it)
+ * and counts [kc] are caller-owned device buffers updated in place; dev_out_assign [n] may be NULL.  With a communicator
+ * every rank passes its shard and all ranks end with identical centroids. */
+int gpann_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_centroids_inout, size_t kc, int rounds, int metric,
+                            int32_t* dev_out_assign, unsigned char* dev_alive_inout, uint64_t* dev_out_counts, void* stream);
 /* sum_i pos_distance(P_i, C_assign[i]) accumulated in double (src/kmeans.cpp:246-249). */
 int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign,
                     int metric, double* out);

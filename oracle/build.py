@@ -75,11 +75,29 @@ def build_ref(force=False):
     return outs
 
 
+def build_router_ref(force=False):
+    """oracle/_ref/libgpann_router_ref.so: tests/integration/router_shim.cpp over the UNMODIFIED reference only
+    (its recall.h, kmeans.cpp, kmeans_tree_router.cpp, defs.cpp, dist.cpp) -- the checker for tests/test_integration.py."""
+    out = os.path.join(REFOUT, "libgpann_router_ref.so")
+    if not have_reference():
+        return out if os.path.exists(out) else None
+    shim = os.path.join(os.path.dirname(HERE), "tests", "integration", "router_shim.cpp")
+    srcs = [shim] + [os.path.join(REF, "src", f) for f in ("kmeans_tree_router.cpp", "kmeans.cpp", "defs.cpp", "dist.cpp")]
+    if not force and _newer(out, srcs):
+        return out
+    os.makedirs(REFOUT, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O3", "-march=x86-64-v3", "-mtune=generic", "-ffast-math", "-fPIC", "-shared", "-pthread",
+                           "-w", "-I" + os.path.join(REF, "src"), "-I" + os.path.join(REF, "external", "parlaylib", "include"), "-o", out,
+                           *srcs])
+    return out
+
+
 def main():
     force = "--force" in sys.argv
     print(build_oracle(force))
     for o in build_ref(force):
         print(o)
+    print(build_router_ref(force))
 
 
 if __name__ == "__main__":
