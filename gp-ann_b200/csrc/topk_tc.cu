@@ -46,6 +46,10 @@
 #ifndef GPANN_DRAIN_ALL
 #define GPANN_DRAIN_ALL 0
 #endif
+// 1: software-pipelined filter loop (one chunk pair of TMEM loads always in flight behind the max trees); 0: the plain loop
+#ifndef GPANN_PIPE
+#define GPANN_PIPE 1
+#endif
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
 #endif
@@ -171,6 +175,49 @@ __device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T
         mask &= mask - 1;
         const uint32_t id = ti[col0 + j];
         if (id != kInvalidId) queue_push(q, ((uint64_t) pick32(v, j) << 32) | id, qs, (uint32_t) tn[col0 + j]);
+    }
+}
+
+// Out-of-line slow path of the PIPELINED filter loop (GPANN_PIPE): the 64 values of a chunk pair sit in the lane's local
+// memory (copied there only when some lane of the warp saw a value reach its threshold), so the hot loop carries one call
+// instead of two inlined select trees per pair and stays small.  Ta / Tb: thresholds of the two 32-column chunks (a chunk
+// whose maximum did not reach the threshold gets "never").  Same records as enqueue_chunk / enqueue_chunk_f.
+template <bool kFloat>
+__device__ __noinline__ void slow_pair(const uint32_t* v, uint32_t Ta_bits, uint32_t Tb_bits, const int32_t* tn, const uint32_t* ti,
+                                       int col0, int nqv, uint32_t qs, uint32_t* q_tail, volatile uint32_t* q_head, uint4* q_rec,
+                                       uint32_t q_cap) {
+    Queue q;
+    q.cap = q_cap;
+    q.rec = q_rec;
+    q.tail = q_tail;
+    q.head = q_head;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t Tbits = half ? Tb_bits : Ta_bits;
+        const uint32_t* vv = v + 32 * half;
+        uint32_t mask = 0;
+        if (kFloat) {
+            const float T = __uint_as_float(Tbits);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(vv[j]) >= T) ? (1u << j) : 0u;
+        } else {
+            const int T = (int) Tbits;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= ((int) vv[j] >= T) ? (1u << j) : 0u;
+        }
+        const int c0 = col0 + 32 * half;
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t id = ti[c0 + j];
+            if (id == kInvalidId) continue;
+            if (kFloat) {
+                queue_push(q, ((uint64_t) vv[j] << 32) | id, qs, (uint32_t) tn[c0 + j]);
+            } else {
+                const int dist = nqv + tn[c0 + j] - 2 * (int) vv[j];
+                queue_push(q, pack_key((float) dist, id), qs);
+            }
+        }
     }
 }
 
@@ -711,6 +758,147 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const uint32_t tbase0 = tmem_base + col_base + lane_sel;
         const int sample_pass = a.sample_pass;
         const float eps = a.eps;
+#if GPANN_PIPE
+        // ===== software-pipelined drain (production path) =====
+        // A filter warp owns 128 columns of every item = two chunk pairs (2 x tcgen05.ld.x32 each).  The loads of the NEXT
+        // pair -- the second pair of this item, or the first pair of the next item -- are issued right after the wait for the
+        // current pair and before its max trees, so one pair is always in flight behind the ALU work (the plain loop exposes
+        // the ~150 clk TMEM round trip twice per item: 650-700 clk per item against 512 clk of MMA).  128 data registers.
+        constexpr bool kPipe = !kProbe && !kFilterByItem && kHalves == 1 && kColsPerWarp == 128 && kSlots == 2 && !GPANN_DRAIN_ALL;
+        if (kPipe && tile_begin < tile_end) {
+            const uint32_t nitems = (tile_end - tile_begin) * (uint32_t) R;
+            uint32_t pa0[32], pa1[32], pb0[32], pb1[32];
+            int r = 0;
+            bool first_of_tile = true;
+            // prologue: item 0, pair 0
+            mbar_wait(bar_tfull, 0);
+            tcgen05_fence_after();
+            tmem_ld32(tbase0, pa0);
+            tmem_ld32(tbase0 + 32, pa1);
+            const int32_t* tn = s_norm;
+            const uint32_t* ti = s_id;
+            int nmin_i = 0;
+            float nmin_f = 0.f, nmax_f = 0.f, rmin_f = 0.f, rmax_f = 0.f;
+            for (uint32_t it = 0; it < nitems; ++it) {
+                const uint32_t bar_te = bar_tempty + 8 * slot;
+                const uint32_t tbase = tbase0 + slot * kAccN;
+                tmem_wait_ld();                       // pair 0 of this item is in registers
+                tmem_ld32(tbase + 64, pb0);           // pair 1 in flight behind pair 0's trees
+                tmem_ld32(tbase + 96, pb1);
+                if (first_of_tile) {                  // the tile's norms / ids arrived with its operands (normally immediate)
+                    mbar_wait(bar_full + 8 * st, ph);
+                    tn = s_norm + st * kTileN;
+                    ti = s_id + st * kTileN;
+                    nmin_i = tn[0];
+                    if (kFloat) {
+                        nmin_f = __int_as_float(tn[0]);
+                        nmax_f = __int_as_float(tn[kAccN - 1]);
+                        rmin_f = sqrtf(nmin_f);
+                        rmax_f = sqrtf(nmax_f);
+                    }
+                }
+                const uint32_t qs = (uint32_t) (r * kTileM + qrow);
+                const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
+                const int nqraw = s_nq[qs];
+                int Ti = 0;
+                float Tf = 0.f;
+                if (kFloat) {  // see the plain loop below for the derivation
+                    const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
+                    const float sq = 2.f * eps * sqrtf(nqv);
+                    const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
+                    const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
+                    float gmin = fminf(g0, g1);
+                    const float nstar = eps * eps * nqv;
+                    if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
+                    Tf = 0.5f * (U + gmin);
+                    Tf -= 1e-6f * fabsf(Tf);
+                } else {
+                    Ti = (Uraw + nmin_i + 1) >> 1;
+                }
+                const bool cold = sample_pass && (kFloat ? Tf < -1.0e37f : Ti < -(1 << 28));
+                // ---- trees of pair 0 (columns col_base + [0,64)) ----
+                {
+                    bool hit;
+                    uint32_t Ta, Tb;
+                    if (kFloat) {
+                        const float ma = max32f(pa0), mb = max32f(pa1);
+                        hit = fmaxf(ma, mb) >= Tf;
+                        Ta = __float_as_uint(ma >= Tf ? (cold ? ma : Tf) : 3.0e38f);
+                        Tb = __float_as_uint(mb >= Tf ? (cold ? mb : Tf) : 3.0e38f);
+                    } else {
+                        const int ma = max32(pa0), mb = max32(pa1);
+                        hit = max(ma, mb) >= Ti;
+                        Ta = (uint32_t) (ma >= Ti ? (cold ? ma : Ti) : 0x7fffffff);
+                        Tb = (uint32_t) (mb >= Ti ? (cold ? mb : Ti) : 0x7fffffff);
+                    }
+                    if (__any_sync(0xffffffffu, hit)) {
+                        ++slow_entries;
+                        if (hit) {
+                            uint32_t tmp[64];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) tmp[j] = pa0[j], tmp[32 + j] = pa1[j];
+                            slow_pair<kFloat>(tmp, Ta, Tb, tn, ti, col_base, nqraw, qs, q.tail, q.head, q.rec, q.cap);
+                        }
+                        __syncwarp();
+                    }
+                }
+                tmem_wait_ld();                       // pair 1 in registers: the accumulator is drained
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_te);   // slot back to the MMA issuer before the arithmetic
+                // advance to the next item and put ITS first pair in flight behind pair 1's trees
+                const bool last_of_tile = r + 1 == R;
+                if (++slot == (uint32_t) kSlots) {
+                    slot = 0;
+                    sph ^= 1;
+                }
+                if (it + 1 < nitems) {
+                    mbar_wait(bar_tfull + 8 * slot, sph);
+                    tcgen05_fence_after();
+                    tmem_ld32(tbase0 + slot * kAccN, pa0);
+                    tmem_ld32(tbase0 + slot * kAccN + 32, pa1);
+                }
+                // ---- trees of pair 1 (columns col_base + [64,128)) ----
+                {
+                    bool hit;
+                    uint32_t Ta, Tb;
+                    if (kFloat) {
+                        const float ma = max32f(pb0), mb = max32f(pb1);
+                        hit = fmaxf(ma, mb) >= Tf;
+                        Ta = __float_as_uint(ma >= Tf ? (cold ? ma : Tf) : 3.0e38f);
+                        Tb = __float_as_uint(mb >= Tf ? (cold ? mb : Tf) : 3.0e38f);
+                    } else {
+                        const int ma = max32(pb0), mb = max32(pb1);
+                        hit = max(ma, mb) >= Ti;
+                        Ta = (uint32_t) (ma >= Ti ? (cold ? ma : Ti) : 0x7fffffff);
+                        Tb = (uint32_t) (mb >= Ti ? (cold ? mb : Ti) : 0x7fffffff);
+                    }
+                    if (__any_sync(0xffffffffu, hit)) {
+                        ++slow_entries;
+                        if (hit) {
+                            uint32_t tmp[64];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) tmp[j] = pb0[j], tmp[32 + j] = pb1[j];
+                            slow_pair<kFloat>(tmp, Ta, Tb, tn, ti, col_base + 64, nqraw, qs, q.tail, q.head, q.rec, q.cap);
+                        }
+                        __syncwarp();
+                    }
+                }
+                first_of_tile = false;
+                ++r;
+                if (last_of_tile) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms / ids
+                    if (++st == (uint32_t) NST) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                    r = 0;
+                    first_of_tile = true;
+                }
+            }
+        } else
+#endif
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
             const long long c0 = stats ? clock64() : 0;
