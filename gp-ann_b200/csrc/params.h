@@ -137,7 +137,8 @@ constexpr bool kATmem = GPANN_A_TMEM != 0;
 constexpr int kATmemCol = kSlots * kAccN;        // first TMEM column of the query tiles (32 columns per 128-byte K block)
 static_assert(kAccN == 128 || kAccN == 256, "accumulator width");
 static_assert(kSlots * kAccN + (kATmem ? 128 : 0) <= kTmemCols, "TMEM budget");
-static_assert(!kFilterByItem || (kEpiWarps == 8 && kSlots == 2 && kAccN == kTileN), "item split: 2 groups of 4 warps, 2 slots");
+static_assert(!kFilterByItem || (kEpiWarps == 8 && ((kSlots == 2 && kAccN == kTileN) || (kSlots == 4 && kAccN == 128))),
+              "item split: 2 groups of 4 warps; 2 slots of 256 columns or 4 slots of 128");
 
 struct Args {
     const void* pnorm;       // [n_pad] ascending squared norms: int32 (bytes) or float (bf16 path)

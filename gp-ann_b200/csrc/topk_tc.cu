@@ -46,9 +46,13 @@
 #ifndef GPANN_DRAIN_ALL
 #define GPANN_DRAIN_ALL 0
 #endif
-// 1: software-pipelined filter loop (one chunk pair of TMEM loads always in flight behind the max trees); 0: the plain loop
+// 1: software-pipelined filter loop (one chunk pair of TMEM loads always in flight behind the max trees); 0: the plain loop.
+// Measured (round 2, profiles/r2_summary.md): SLOWER, 150 vs 96 ms at 100M -- with the next item's loads queued behind the
+// wait for ITS accumulator, every slow-path entry and both tree pairs sit between an accumulator's arrival and the release
+// of its slot, the MMA issuer starves (ncu: 52 % of the filter warps' samples on the accumulator wait) and the restructured
+// loop carries 244 instead of ~130 instructions per warp and item.  Kept as a build knob.
 #ifndef GPANN_PIPE
-#define GPANN_PIPE 1
+#define GPANN_PIPE 0
 #endif
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
@@ -676,7 +680,35 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 ph ^= 1;
             }
         }
-        for (uint32_t t = tile_begin; !fast_issue && t < tile_end; ++t) {
+        // The same for 128-column accumulators in four slots (GPANN_ACC_N=128 GPANN_SLOTS=4): 8 items per tile, item j = (query
+        // tile j >> 1, point half j & 1) in slot j & 3; a slot is used twice per tile, so the parities are constants again.
+        const bool fast_issue8 = !kProbe && R == 4 && nks == 4 && KB == 1 && kHalves == 2 && kSlots == 4;
+        for (uint32_t t = tile_begin; fast_issue8 && t < tile_end; ++t) {
+            mbar_wait(bar_full + 8 * st, ph);
+            tcgen05_fence_after();
+            const uint64_t b_st = b_base + ((st * p_tile_bytes) >> 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                mbar_wait(bar_tempty + 8 * (j & 3), ((j >> 2) & 1) ^ 1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t dcol = tmem_base + (j & 3) * kAccN;
+                    const uint64_t a_r = a_base + (uint32_t) ((j >> 1) * (kQBlockBytes >> 4));
+                    const uint64_t b_h = b_st + (uint32_t) ((j & 1) * ((kAccN * kRowBytes) >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) issue_mma<kFloat>(dcol, a_r + 2 * ks, b_h + 2 * ks, 0, tmem_base, idesc, ks > 0);
+                    umma_commit(bar_tfull + 8 * (j & 3));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar_empty + 8 * st);
+            __syncwarp();
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        for (uint32_t t = tile_begin; !fast_issue && !fast_issue8 && t < tile_end; ++t) {
             const long long c0 = stats ? clock64() : 0;
             mbar_wait(bar_full + 8 * st, ph);
             if (stats) w_full += clock64() - c0;
@@ -764,8 +796,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         // pair -- the second pair of this item, or the first pair of the next item -- are issued right after the wait for the
         // current pair and before its max trees, so one pair is always in flight behind the ALU work (the plain loop exposes
         // the ~150 clk TMEM round trip twice per item: 650-700 clk per item against 512 clk of MMA).  128 data registers.
-        constexpr bool kPipe = !kProbe && !kFilterByItem && kHalves == 1 && kColsPerWarp == 128 && kSlots == 2 && !GPANN_DRAIN_ALL;
-        if (kPipe && tile_begin < tile_end) {
+        constexpr bool kPipe = !kFilterByItem && kHalves == 1 && kColsPerWarp == 128 && kSlots == 2 && !GPANN_DRAIN_ALL;
+        if (kPipe && mode == 0 && tile_begin < tile_end) {
             const uint32_t nitems = (tile_end - tile_begin) * (uint32_t) R;
             uint32_t pa0[32], pa1[32], pb0[32], pb1[32];
             int r = 0;
@@ -786,7 +818,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 tmem_ld32(tbase + 64, pb0);           // pair 1 in flight behind pair 0's trees
                 tmem_ld32(tbase + 96, pb1);
                 if (first_of_tile) {                  // the tile's norms / ids arrived with its operands (normally immediate)
+                    const long long c0 = stats ? clock64() : 0;
                     mbar_wait(bar_full + 8 * st, ph);
+                    if (stats) w_pfull += clock64() - c0;
                     tn = s_norm + st * kTileN;
                     ti = s_id + st * kTileN;
                     nmin_i = tn[0];
@@ -853,7 +887,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                     sph ^= 1;
                 }
                 if (it + 1 < nitems) {
+                    const long long c1 = stats ? clock64() : 0;
                     mbar_wait(bar_tfull + 8 * slot, sph);
+                    if (stats) w_tfull += clock64() - c1;
                     tcgen05_fence_after();
                     tmem_ld32(tbase0 + slot * kAccN, pa0);
                     tmem_ld32(tbase0 + slot * kAccN + 32, pa1);
@@ -923,7 +959,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                 for (int h = 0; h < kHalves; ++h) {
                     const uint32_t bar_tf = bar_tfull + 8 * slot, bar_te = bar_tempty + 8 * slot, par_tf = sph;
                     const uint32_t tbase = tbase0 + slot * kAccN;
-                    const bool mine = !kFilterByItem || slot == (uint32_t) half;
+                    const bool mine = !kFilterByItem || (slot & 1u) == (uint32_t) half;  // by item: group g takes the slots of parity g
                     if (++slot == (uint32_t) kSlots) {
                         slot = 0;
                         sph ^= 1;
