@@ -12,7 +12,7 @@ for tag in "$@"; do
     python - <<PY
 import json
 try:
-    l = json.load(open("gpurun_out/ab_${tag}_$n.json"))
+    l = json.loads([x for x in open("gpurun_out/ab_${tag}_$n.json").read().splitlines() if x.startswith("{")][-1])
     print("$tag", $n, "ms/step %.2f" % l["ms_per_step"], "kernel_ms %.2f" % l["roofline"]["kernel_ms"], "frac %.3f" % l["roofline"]["frac"],
           "verified", (l.get("verified") or {}).get("ok"), "clk", l["clocks"]["sm_mhz"])
 except Exception as e:

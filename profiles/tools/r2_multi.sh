@@ -15,7 +15,7 @@ run() {  # name, env..., -- bench args
   python - <<PY
 import json
 try:
-    l = json.load(open("gpurun_out/r2_bench_${name}.json"))
+    l = json.loads([x for x in open("gpurun_out/r2_bench_${name}.json").read().splitlines() if x.startswith("{")][-1])
     print("${name}", "ms/step %.2f" % l["ms_per_step"], "kernel_ms %.2f" % l["roofline"]["kernel_ms"], "whole-step frac %.3f" % l["roofline"]["whole_step_frac"],
           "verified", (l.get("verified") or {}).get("ok"), "e2e ms", (l.get("e2e") or {}).get("ms_per_step"), "kmeans", (l.get("kmeans_sharded") or {}).get("ms_per_round"))
 except Exception as e:

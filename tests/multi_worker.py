@@ -86,10 +86,11 @@ def main():
     assign = torch.empty(khi - klo, dtype=torch.int32, device=dev)
     ctx.kmeans_run_device(kpts, cent.data_ptr(), kc, 5, alive.data_ptr(), counts.data_ptr(), dev_assign=assign.data_ptr(), stream=st)
     torch.cuda.synchronize()
-    assert int(counts.sum().item()) == kn and int(alive.sum().item()) == kc - 4
+    assert int(counts.sum().item()) == kn
     with gpann.Context(local) as solo:  # the whole set on one GPU
         a1, c1, s1 = solo.kmeans_run(solo.upload(X, storage=gpann.STORAGE_F32), C0, rounds=5)
     live = alive.cpu().numpy().astype(bool)
+    assert int(live.sum()) == len(c1) <= kc - 4  # the four far-away seeds (at least) lose every member
     np.testing.assert_allclose(cent.cpu().numpy()[live], c1, rtol=1e-5, atol=1e-5)
     assert np.array_equal(counts.cpu().numpy()[live].astype(np.uint64), s1)
     remap = np.cumsum(live) - 1
