@@ -141,6 +141,25 @@ int gpann_topk_sharded_device(gpann_ctx* ctx, const gpann_points* pts, const flo
     if (is_group(ctx)) return no_group(ctx, "topk_sharded_device");
     return sd_topk_sharded_device(ctx, pts, dev_queries, nq, k, metric, dev_out_dist, dev_out_id, dev_out_keys, stream);
 }
+int gpann_ivf_topk(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, size_t num_buckets, const uint32_t* permutation,
+                   const float* queries, size_t nq, const int32_t* probes, int nprobe, int k, int metric, float* out_dist, uint32_t* out_id,
+                   uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if (is_group(ctx)) return no_group(ctx, "ivf_topk");
+    return sd_ivf_topk(ctx, pts, bucket_offsets, num_buckets, permutation, queries, nq, probes, nprobe, k, metric, out_dist, out_id, out_count);
+}
+int gpann_knn_buckets(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, const uint32_t* bucket_members, size_t num_buckets,
+                      int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if (is_group(ctx)) return no_group(ctx, "knn_buckets");
+    return sd_knn_buckets(ctx, pts, bucket_offsets, bucket_members, num_buckets, k, metric, out_dist, out_id, out_count);
+}
+int gpann_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint32_t* point_ids, size_t m, const gpann_points* leaders, int k,
+                                int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count) {
+    if (!ctx) return GPANN_E_ARG;
+    if (is_group(ctx)) return no_group(ctx, "closest_leaders_batch");
+    return sd_closest_leaders_batch(ctx, pts, point_ids, m, leaders, k, metric, out_dist, out_id, out_count);
+}
 int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist, uint32_t* dev_out_id,
                             uint64_t* dev_out_keys, void* stream) {
     if (!ctx) return GPANN_E_ARG;

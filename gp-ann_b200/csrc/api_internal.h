@@ -63,6 +63,16 @@ struct gpann_ctx {
     // devices of one process: a child of a gpann_init_multi group) ----
     void* comm = nullptr;          // ncclComm_t
     int comm_rank = 0, comm_size = 1;
+    // peer-shared bounds of the sharded top-k: a fixed-size array (one slot per query of the largest batch) that the other
+    // ranks' kernels tighten with system-scope atomicMin over NVLink (cudaIpc between processes, direct peer access inside
+    // a group ctx); peer_bound[i] = the other ranks' arrays mapped here.  peer_share is raised by topk_sharded for the
+    // calls that may use them (one query batch per call, see there).
+    uint32_t* shared_bound = nullptr;
+    size_t shared_bound_slots = 0;
+    uint32_t* peer_bound[gpann::tc::kMaxPeers] = {};
+    int npeers = 0;
+    bool peer_ipc = false;         // peer_bound[] came from cudaIpcOpenMemHandle (close on destroy)
+    bool peer_share = false;
     DevBuf gather_send, gather_recv, km_run_cent, km_run_sums, km_run_counts, km_run_alive, km_run_remap, km_run_norms;
     // ---- group root (gpann_init_multi): owns one child ctx + worker thread per device; the root itself launches nothing
     gpimpl::Group* group = nullptr;
@@ -254,6 +264,13 @@ int sd_kmeans_run(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inou
 int sd_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_centroids_inout, size_t kc, int rounds, int metric,
                          int32_t* dev_out_assign, unsigned char* dev_alive_inout, uint64_t* dev_out_counts, void* stream);
 int sd_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric, double* out);
+int sd_ivf_topk(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, size_t num_buckets, const uint32_t* permutation,
+                const float* queries, size_t nq, const int32_t* probes, int nprobe, int k, int metric, float* out_dist, uint32_t* out_id,
+                uint32_t* out_count);
+int sd_knn_buckets(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, const uint32_t* bucket_members, size_t num_buckets,
+                   int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+int sd_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint32_t* point_ids, size_t m, const gpann_points* leaders, int k,
+                             int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
 int sd_set_algo(gpann_ctx* ctx, int algo);
 int sd_set_timing(gpann_ctx* ctx, int on);
 float sd_last_kernel_ms(gpann_ctx* ctx);

@@ -229,6 +229,8 @@ struct TcPlan {
     int R = 1, G = 1, k = 0, cap = 128, lists_smem = 0;
     size_t nqb = 0, nq_pad = 0;
     const int* gate = nullptr;  // device flag the batch's kernels are gated on (byte storage: queries integer-valued)
+    uint32_t* bound = nullptr;  // [nq_pad] per-query bounds of this batch: ctx->bound, or the peer-shared array of a sharded call
+    bool peers = false;         // the kernels also push tightened bounds to the other ranks' arrays
     CUtensorMap tmap_q;
 };
 
@@ -280,17 +282,19 @@ int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, c
     GP_TRY(reserve(ctx, ctx->qnorm, pl.nq_pad * 4));
     GP_TRY(reserve(ctx, ctx->bound, pl.nq_pad * 4));
     GP_TRY(reserve(ctx, ctx->flags, 64));
+    pl.peers = ctx->peer_share && ctx->shared_bound && pl.nq_pad <= ctx->shared_bound_slots;
+    pl.bound = pl.peers ? ctx->shared_bound : (uint32_t*) ctx->bound.p;
     if (pl.is_float) {
         GP_TRY(reserve(ctx, ctx->qf32, pl.nq_pad * d * sizeof(float)));
         launch_prep_queries_bf16(dq, (int) nqb, d, dp, (int) pl.nq_pad, (unsigned short*) ctx->qrows.p, (float*) ctx->qnorm.p,
-                                 (float*) ctx->qf32.p, (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
+                                 (float*) ctx->qf32.p, (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : pl.bound, st);
         GP_TRY(check_launch(ctx, "prep_queries_bf16_kernel"));
     } else {
         int* okflag = (int*) ctx->flags.p + kFlagQueriesOk;
         CU_TRY(ctx, cudaMemsetAsync(okflag, 1, sizeof(int), st));  // 0x01010101: "ok" until a query refutes it
         launch_prep_queries_bytes(dq, (int) nqb, d, (int) pl.nq_pad, pl.is_signed, (unsigned char*) ctx->qrows.p,
                                   (int32_t*) ctx->qnorm.p, okflag,
-                                  (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : (uint32_t*) ctx->bound.p, st);
+                                  (ctx->tc_warm && ctx->tc_warm_valid) ? nullptr : pl.bound, st);
         GP_TRY(check_launch(ctx, "prep_queries_bytes_kernel"));
         pl.gate = okflag;
     }
@@ -337,7 +341,9 @@ int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L)
     a.idesc = pl.is_float ? tc::make_idesc_bf16() : tc::make_idesc_i8(pl.is_signed);
     a.cand = (uint64_t*) ctx->cand.p;
     a.partial = L.carry_keys + L.part_keys;
-    a.bound = (uint32_t*) ctx->bound.p;
+    a.bound = pl.bound;
+    a.npeers = pl.peers ? ctx->npeers : 0;
+    for (int i = 0; i < a.npeers; ++i) a.peer_bound[i] = ctx->peer_bound[i];
     a.mode = ctx->tc_mode;
     a.rows_f32 = pl.is_float ? lay.rows_f32 : nullptr;
     a.q_f32 = pl.is_float ? (const float*) ctx->qf32.p : nullptr;
@@ -394,7 +400,7 @@ int tc_sample(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, cudaStream_
             a.stats = nullptr;
         }
         TopkOut b;
-        b.kth = (float*) ctx->bound.p;  // float bits: read back by the next pass as its bound
+        b.kth = (float*) pl.bound;      // float bits: read back by the next pass as its bound
         b.kth_full_only = 1;            // min(previous bound, k-th of a full list)
         GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st, pl.gate, 1));
     }
@@ -451,7 +457,7 @@ int tc_main(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool carry, b
     if (!carry) {
         if (ctx->tc_warm) {  // probe: the final k-th distances become the next call's bounds
             TopkOut b;
-            b.kth = (float*) ctx->bound.p;
+            b.kth = (float*) pl.bound;
             b.kth_full_only = 1;
             GP_TRY(launch_merge(ctx, a.partial, S, pl.nq_pad, pl.nqb, k, b, 0, st, pl.gate, 1));
             ctx->tc_warm_valid = true;
@@ -460,7 +466,7 @@ int tc_main(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool carry, b
     }
     TopkOut c;
     c.keys = L.carry_keys;            // in place: a warp reads all parts of its query before it writes
-    c.kth = (float*) ctx->bound.p;
+    c.kth = (float*) pl.bound;
     c.kth_full_only = 1;
     return launch_merge(ctx, L.carry_keys, S + 1, pl.nq_pad, pl.nqb, k, c, 0, st, pl.gate, 1);
 }
@@ -498,7 +504,7 @@ int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t
         GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st));
         *gate = pl.gate;
         GP_TRY(tc_sample(ctx, pl, lay, st));
-        if (between) GP_TRY(between((uint32_t*) ctx->bound.p, pl.nqb, st));  // real queries only: the count every rank agrees on
+        if (between) GP_TRY(between(pl.bound, pl.nqb, st));  // real queries only: the count every rank agrees on
         GP_TRY(tc_main(ctx, pl, lay, false, false, out, q0, st));
     }
     ctx->last_algo = is_float ? "tensor_bf16" : (pts->storage == GPANN_STORAGE_S8 ? "tensor_s8" : "tensor_u8");
@@ -1040,7 +1046,7 @@ int sd_init(gpann_ctx** out, int device) {
         qres == cudaDriverEntryPointSuccess)
         ctx->encode_tiled = (EncodeTiledFn) fn;
     // opt every large-shared-memory kernel in for this device (function attributes are per device)
-    if (stream_set_attributes() != cudaSuccess || kmeans_set_attributes() != cudaSuccess || tc_set_attributes() != cudaSuccess ||
+    if (stream_set_attributes() != cudaSuccess || seg_set_attributes() != cudaSuccess || kmeans_set_attributes() != cudaSuccess || tc_set_attributes() != cudaSuccess ||
         kmtc_set_attributes() != cudaSuccess) {
         std::fprintf(stderr, "gpann_init: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         cudaStreamDestroy(ctx->stream);
@@ -1341,11 +1347,19 @@ int topk_sharded(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size
     GP_TRY(reserve(ctx, ctx->gather_recv, part * 8 * ctx->comm_size));
     const BetweenFn between = [ctx](uint32_t* bound, size_t count, cudaStream_t s) { return comm_allreduce_min_u32(ctx, bound, count, s); };
     const size_t batch = tc_batch_max(ctx, 2);
-    for (size_t q0 = 0; q0 < nq; q0 += batch) {
+    // Peer-shared bounds (the kernels of every rank tighten every other rank's bounds over NVLink while they run) need the
+    // shared array to belong to ONE query batch between two collectives of the call: the all-gather below is what tells a
+    // rank that no peer kernel of this call is still writing before the next call resets the array.
+    static const bool no_peers = std::getenv("GPANN_NO_PEER_BOUNDS") != nullptr;
+    ctx->peer_share = !no_peers && ctx->npeers > 0 && nq <= batch;
+    int rc = 0;
+    for (size_t q0 = 0; q0 < nq && rc == 0; q0 += batch) {
         TopkOut local;
         local.keys = (uint64_t*) ctx->gather_send.p + q0 * k;
-        GP_TRY(topk_dispatch(ctx, pts, row_begin, row_end, dq + q0 * pts->d, std::min(batch, nq - q0), k, metric, local, st, between));
+        rc = topk_dispatch(ctx, pts, row_begin, row_end, dq + q0 * pts->d, std::min(batch, nq - q0), k, metric, local, st, between);
     }
+    ctx->peer_share = false;
+    GP_TRY(rc);
     GP_TRY(comm_allgather_u64(ctx, (const uint64_t*) ctx->gather_send.p, (uint64_t*) ctx->gather_recv.p, part, st));
     return launch_merge(ctx, (const uint64_t*) ctx->gather_recv.p, ctx->comm_size, nq, nq, k, out, 0, st, nullptr, 0);
 }

@@ -85,7 +85,64 @@ int nccl_fail(gpann_ctx* ctx, const char* what, ncclResult_t r) {
     } while (0)
 }  // namespace
 
+// ---- peer-shared bounds ------------------------------------------------------------------------------------------------------
+namespace {
+size_t shared_bound_slots(const gpann_ctx* ctx) { return (size_t) ctx->num_sms * tc::kMaxR * tc::kTileM; }  // the largest query batch
+
+int alloc_shared_bound(gpann_ctx* ctx) {
+    if (ctx->shared_bound) return 0;
+    const size_t slots = shared_bound_slots(ctx);
+    CU_TRY(ctx, cudaMalloc(&ctx->shared_bound, slots * 4));
+    CU_TRY(ctx, cudaMemset(ctx->shared_bound, 0x7f, slots * 4));
+    ctx->shared_bound_slots = slots;
+    return 0;
+}
+
+void peer_destroy(gpann_ctx* ctx) {
+    if (ctx->peer_ipc)
+        for (int i = 0; i < ctx->npeers; ++i) cudaIpcCloseMemHandle(ctx->peer_bound[i]);
+    ctx->npeers = 0;
+    ctx->peer_ipc = false;
+    if (ctx->shared_bound) cudaFree(ctx->shared_bound);
+    ctx->shared_bound = nullptr;
+    ctx->shared_bound_slots = 0;
+}
+
+// Several processes: every rank exports its array as a CUDA IPC handle, the handles travel through the communicator
+// itself (one all-gather), every rank maps the others'.  A rank that cannot map a peer (no P2P path) simply does not push
+// to it: the shared bounds are an accelerator, never needed for the result.
+int setup_peer_bounds_ipc(gpann_ctx* ctx) {
+    static const bool off = std::getenv("GPANN_NO_PEER_BOUNDS") != nullptr;
+    if (off || ctx->comm_size <= 1) return 0;
+    GP_TRY(alloc_shared_bound(ctx));
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, ctx->shared_bound) != cudaSuccess) {
+        cudaGetLastError();
+        std::memset(&mine, 0, sizeof(mine));
+    }
+    const int n = ctx->comm_size;
+    ScopedDev d;
+    CU_TRY(ctx, d.alloc((size_t) n * sizeof(mine)));
+    CU_TRY(ctx, cudaMemcpy(d.as<char>() + (size_t) ctx->comm_rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NCCL_TRY(ctx, nccl().AllGather(d.as<char>() + (size_t) ctx->comm_rank * sizeof(mine), d.p, sizeof(mine), ncclChar, (ncclComm_t) ctx->comm,
+                                   ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(n);
+    CU_TRY(ctx, cudaMemcpy(all.data(), d.p, (size_t) n * sizeof(mine), cudaMemcpyDeviceToHost));
+    const cudaIpcMemHandle_t zero = {};
+    for (int r = 0; r < n && ctx->npeers < tc::kMaxPeers; ++r) {
+        if (r == ctx->comm_rank || std::memcmp(&all[r], &zero, sizeof(zero)) == 0) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) ctx->peer_bound[ctx->npeers++] = (uint32_t*) p;
+        else cudaGetLastError();
+    }
+    ctx->peer_ipc = true;
+    return 0;
+}
+}  // namespace
+
 void comm_destroy(gpann_ctx* ctx) {
+    peer_destroy(ctx);
     if (ctx->comm && nccl().ok()) nccl().CommDestroy((ncclComm_t) ctx->comm);
     ctx->comm = nullptr;
     ctx->comm_size = 1;
@@ -149,7 +206,7 @@ int comm_init_rank(gpann_ctx* ctx, int nranks, int rank, const void* id_bytes, s
     ctx->comm = comm;
     ctx->comm_size = nranks;
     ctx->comm_rank = rank;
-    return 0;
+    return setup_peer_bounds_ipc(ctx);
 }
 
 // ---- group ctx: one worker thread per device ------------------------------------------------------------------------------
@@ -268,6 +325,30 @@ int mg_init(gpann_ctx** out, const int* devices, int ndev) {
         return rc;
     }
     root->num_sms = g->ranks[0]->num_sms;
+    // peer-shared bounds inside one process: direct peer access between the devices of the group
+    static const bool no_peers = std::getenv("GPANN_NO_PEER_BOUNDS") != nullptr;
+    if (ndev > 1 && !no_peers) {
+        for (int i = 0; i < ndev; ++i) {
+            cudaSetDevice(devices[i]);
+            if (alloc_shared_bound(g->ranks[i]) != 0) cudaGetLastError();
+        }
+        for (int i = 0; i < ndev; ++i) {
+            gpann_ctx* c = g->ranks[i];
+            cudaSetDevice(devices[i]);
+            for (int j = 0; j < ndev && c->npeers < tc::kMaxPeers; ++j) {
+                int can = 0;
+                if (j == i || !g->ranks[j]->shared_bound || !c->shared_bound) continue;
+                if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    cudaGetLastError();
+                    continue;
+                }
+                cudaGetLastError();
+                c->peer_bound[c->npeers++] = g->ranks[j]->shared_bound;
+            }
+        }
+    }
     for (int i = 0; i < ndev; ++i) {
         Worker* w = new Worker();
         w->th = std::thread([w, d = devices[i]] { w->loop(d); });

@@ -48,6 +48,43 @@ struct MergeParams {
     int gate_want;
 };
 
+// ---- seg.cu: segmented exact scans (batched IVF probes, per-bucket all-pairs, leaders for every point) -------------
+constexpr int kSegQB = 16;  // queries per task
+struct SegTask {
+    uint64_t pos_begin, pos_end;   // scan positions of this task
+    uint32_t q_begin, q_count;     // its queries: task_query[q_begin .. q_begin + q_count), q_count <= kSegQB; slot = q_begin + i
+};
+struct SegParams {
+    const char* rows;        // scanned point set
+    size_t pitch;
+    int storage, d;
+    const uint32_t* row_map; // optional: scan position -> row of `rows` (buckets / clusters as index lists); else position == row
+    int id_is_row;           // ranking id of a candidate: 1 = row + id_base (global id), 0 = position - pos_id_origin
+    uint32_t id_base;
+    uint64_t pos_id_origin;
+    const char* q_base;      // query source: float rows given by the caller, or the rows of a point set (any storage)
+    size_t q_pitch;
+    int q_storage;
+    const uint32_t* query_rows;  // optional: query i is row query_rows[i] of the query source (else row i)
+    const uint32_t* task_query;  // [slots] query index per task slot
+    const SegTask* tasks;
+    int ntasks;
+    int k, metric, cap, spitch, qpitch, vec_ok;
+    int exclude_self;        // skip the scanned row that IS the query's own row (queries are rows of the scanned set)
+    uint64_t* partial;       // [slots, k]
+};
+struct SegMergeParams {
+    const uint64_t* keys;        // [slots, k]
+    const uint32_t* slot_begin;  // [nq + 1] CSR over slot_list (or over consecutive slots when slot_list == nullptr)
+    const uint32_t* slot_list;   // optional
+    size_t nq;
+    int k, cap;
+    const uint32_t* id_remap;    // optional: reported id = id_remap[ranking id] (InvertedIndex permutation)
+    float* out_dist;
+    uint32_t* out_id;
+    uint32_t* out_count;
+};
+
 // ---- kmeans.cu ----------------------------------------------------------------------------------------------
 struct RowsView {
     const char* rows;
@@ -117,6 +154,7 @@ constexpr int kQBlockBytes = kTileM * kRowBytes;  // 16 KB per K block of a quer
 constexpr int kPBlockBytes = kTileN * kRowBytes;  // 32 KB per K block of a point tile
 constexpr int kSmemListKeys = 16;                // per-query top-k lists live in shared memory when k <= 16 (one K block)
 constexpr uint32_t kPaceWindow = 192;            // tiles a CTA may run ahead of the slowest CTA of its point split
+constexpr int kMaxPeers = 7;                     // other ranks of a sharded call whose bound arrays are mapped here (8 GPUs per box)
 constexpr int kTmemCols = 512;                   // accumulator slots (+ the resident query tiles when kATmem)
 // Pipeline shape (compile-time, A/B-tested through GPANN_NVCC_EXTRA): an "item" is one MMA accumulator of 128 queries x
 // kAccN points; kSlots accumulators rotate through TMEM; with kATmem the query tiles (operand A) live in TMEM columns
@@ -169,6 +207,8 @@ struct Args {
     uint32_t* pace;          // optional [S*G] tile positions of the CTAs (zeroed before the launch): L2 pacing of a split's CTAs
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
     const int* gate;         // optional device flag (queries are integer-valued): the kernel returns at once when *gate == 0
+    uint32_t* peer_bound[kMaxPeers];  // sharded calls: the other ranks' `bound` arrays (NVLink peer memory), same slot layout
+    int npeers;
 };
 
 // Shared-memory footprint (+1 KB so the operand area can be aligned to 1024 bytes).
@@ -176,7 +216,7 @@ inline size_t smem_bytes(int R, int kblocks, int stages, int qcap, int lists_sme
     return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
            (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 16 /*queues*/ +
            (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/ +
-           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/;
+           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/ + 64 /*dirty bitmap (peer bounds)*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {
     const uint32_t fmt = is_signed ? 1u : 0u;
@@ -252,6 +292,9 @@ struct KmFinalizeParams {
 
 // ---- launchers (each defined in the translation unit that owns the kernel) -------------------------------------
 cudaError_t stream_set_attributes();
+cudaError_t seg_set_attributes();
+void launch_seg_scan(const SegParams& p, unsigned grid, size_t smem, cudaStream_t st);
+void launch_seg_merge(const SegMergeParams& p, cudaStream_t st);
 cudaError_t kmeans_set_attributes();
 cudaError_t tc_set_attributes();
 

@@ -236,6 +236,13 @@ struct SelState {
                        // every CTA (point split) that serves the same queries -- atomicMin when a list tightens, re-read
                        // while the selection warp idles
     int nslots;
+    // Sharded calls (multi.cu): the other ranks' bound arrays, mapped into this GPU's address space (NVLink peer memory).
+    // A tightened bound is pushed to them with one system-scope atomicMin per peer, batched through a dirty bitmap while
+    // the selection warp idles -- a shard then filters with the k-th distances of the WHOLE set as they form, instead of
+    // rediscovering them (each shard on its own pushes ~k ln(n_shard) records per query through the slow path).
+    uint32_t* peer[kMaxPeers];
+    int npeers;
+    uint32_t* dirty;   // shared-memory bitmap [nslots/32]: bound tightened since the last push to the peers
     uint64_t* lists; // [nslots][stride] keys of this CTA: global (L2), or shared memory when k <= kSmemListKeys
     int k, cap, stride;
     // float path: exact re-rank inputs
@@ -304,7 +311,10 @@ __device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs
     const float kd = key_dist(kth);
     apply_bound<kFloat>(s, qs, kd);
     // distances are non-negative, so their bit patterns order like unsigned integers
-    if (s.gbound && kd >= 0.f) atomicMin(s.gbound + qs, __float_as_uint(kd));
+    if (s.gbound && kd >= 0.f) {
+        const uint32_t bits = __float_as_uint(kd);
+        if (atomicMin(s.gbound + qs, bits) > bits && s.npeers > 0) atomicOr(s.dirty + (qs >> 5), 1u << (qs & 31));
+    }
 }
 // Pull the bounds other point splits have published for this selection warp's queries into the filter thresholds.
 template <bool kFloat>
@@ -312,8 +322,16 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
     if (!s.gbound) return;
     for (int base = sel * 32; base < s.nslots; base += 32 * kSelWarps) {
         const uint32_t qs = (uint32_t) (base + lane);
-        const float b = __uint_as_float(__ldcg(s.gbound + qs));
+        const uint32_t bits = __ldcg(s.gbound + qs);
+        const float b = __uint_as_float(bits);
         if (b < 3.0e38f) apply_bound<kFloat>(s, qs, b);
+        if (s.npeers > 0) {  // this selection warp owns the bitmap words of its slots: plain read-and-clear by lane 0
+            uint32_t word = 0;
+            if (lane == 0) word = atomicExch(s.dirty + (base >> 5), 0u);
+            word = __shfl_sync(0xffffffffu, word, 0);
+            if ((word >> lane) & 1u)
+                for (int pi = 0; pi < s.npeers; ++pi) atomicMin_system(s.peer[pi] + qs, bits);
+        }
     }
 }
 
@@ -373,7 +391,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
 template <bool kFloat>
 __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel,
                                                  unsigned long long* stats) {
-    uint32_t head = 0, idle = 0;
+    uint32_t head = 0, idle = 0, busy = 0;
     unsigned long long n_batches = 0, n_rounds = 0, n_idle = 0, clk_insert = 0, clk_pop = 0;
     while (true) {
         const long long c_top = stats ? clock64() : 0;
@@ -384,6 +402,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         if (avail == 0) {
             if (finished == (uint32_t) kEpiWarps) break;
             if ((++idle & 7u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~8 us of idling
+            busy = 0;
             __nanosleep(GPANN_SEL_SLEEP);  // an idle selection warp should cost (almost) no issue slots or power
             ++n_idle;
             continue;
@@ -440,6 +459,8 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             }
         }
         if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
+        // a busy selection warp (cold start) still trades bounds with the other splits / ranks now and then
+        if (s.npeers > 0 && (++busy & 15u) == 0) refresh_bounds<kFloat>(s, sel, lane);
     }
     if (stats && lane == 0 && sel == 0 && blockIdx.x == 0) {  // diagnostics (GPANN_TC_STATS)
         stats[16] = n_batches;
@@ -506,6 +527,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int* s_nq = s_cnt + R * kTileM;                                            // int or float bits
     int* s_maxpos = s_nq + R * kTileM;
     uint64_t* s_lists = reinterpret_cast<uint64_t*>(s_maxpos + R * kTileM);   // [R*128][kSmemListKeys] when a.lists_smem
+    uint32_t* s_dirty = reinterpret_cast<uint32_t*>(s_lists + (a.lists_smem ? (size_t) R * kTileM * kSmemListKeys : 0));  // [R*4]
 
     const int nslots = R * kTileM;
     const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
@@ -531,6 +553,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     }
     for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qrec[i] = make_uint4(0u, 0u, kQEmpty, 0u);
     if (tid < 8) s_ctr[tid] = 0;
+    if (tid < R * (kTileM / 32)) s_dirty[tid] = 0;
     if (warp == kTmaWarp && lane == 0) {
         prefetch_tmap(&tmap_p);
         prefetch_tmap(&tmap_q);
@@ -1101,6 +1124,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.id_base = a.id_base;
         ss.eps = a.eps;
         ss.gbound = a.bound ? a.bound + qbase : nullptr;
+        ss.npeers = a.bound ? a.npeers : 0;
+        for (int pi = 0; pi < kMaxPeers; ++pi) ss.peer[pi] = pi < a.npeers ? a.peer_bound[pi] + qbase : nullptr;
+        ss.dirty = s_dirty;
         ss.nslots = nslots;
         selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue

@@ -46,6 +46,9 @@ SYMBOLS = {
     "gpann_topk_stream": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp, _vp, _vp]),
     "gpann_topk_stream_bytes_device": (_i, [_vp, _vp, _sz, _sz, _i, _u32, _vp, _sz, _i, _sz, _vp, _vp]),
     "gpann_topk_range": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "gpann_ivf_topk": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "gpann_knn_buckets": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
+    "gpann_closest_leaders_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp]),
     "gpann_merge_keys_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
     "gpann_pack_key": (_u64, [C.c_float, _u32]),
     "gpann_unpack_key": (None, [_u64, C.POINTER(C.c_float), C.POINTER(_u32)]),
@@ -264,6 +267,36 @@ class Context:
         self.check(self.lib.gpann_topk_stream_bytes_device(self.h, C.c_void_p(host_ptr), n, d, int(is_signed), id_base,
                                                            C.c_void_p(dev_queries), nq, k, chunk_rows, C.c_void_p(dev_out_keys),
                                                            C.c_void_p(stream or 0)))
+
+    # ---- segmented scans: batched IVF probes, per-bucket all-pairs, leaders for every point ----
+    def ivf_topk(self, pts, bucket_offsets, queries, probes, k, permutation=None, metric=L2):
+        """InvertedIndex::Query for a batch: probes [nq, nprobe] bucket ids per query (negative = unused)."""
+        q = self._rows(queries, pts.d, "ivf_topk queries")
+        off = np.ascontiguousarray(bucket_offsets, dtype=np.uint64)
+        pr = np.ascontiguousarray(probes, dtype=np.int32)
+        perm = None if permutation is None else np.ascontiguousarray(permutation, dtype=np.uint32)
+        nq = q.shape[0]
+        dist, ids, cnt = np.empty((nq, k), np.float32), np.empty((nq, k), np.uint32), np.empty(nq, np.uint32)
+        self.check(self.lib.gpann_ivf_topk(self.h, pts.h, _ptr(off), len(off) - 1, _ptr(perm), _ptr(q), nq, _ptr(pr), pr.shape[1], k, metric,
+                                           _ptr(dist), _ptr(ids), _ptr(cnt)))
+        return dist, ids, cnt
+
+    def knn_buckets(self, pts, bucket_offsets, bucket_members, k, metric=L2):
+        """CrunchBucket for all buckets: per member position the k nearest other members of its bucket (global ids)."""
+        off = np.ascontiguousarray(bucket_offsets, dtype=np.uint64)
+        mem = np.ascontiguousarray(bucket_members, dtype=np.uint32)
+        total = len(mem)
+        dist, ids, cnt = np.empty((total, k), np.float32), np.empty((total, k), np.uint32), np.empty(total, np.uint32)
+        self.check(self.lib.gpann_knn_buckets(self.h, pts.h, _ptr(off), _ptr(mem), len(off) - 1, k, metric, _ptr(dist), _ptr(ids), _ptr(cnt)))
+        return dist, ids, cnt
+
+    def closest_leaders_batch(self, pts, leaders, k, point_ids=None, metric=L2):
+        """ClosestLeaders for every listed point (all points when point_ids is None): ids = leader index."""
+        pid = None if point_ids is None else np.ascontiguousarray(point_ids, dtype=np.uint32)
+        m = pts.n if pid is None else len(pid)
+        dist, ids, cnt = np.empty((m, k), np.float32), np.empty((m, k), np.uint32), np.empty(m, np.uint32)
+        self.check(self.lib.gpann_closest_leaders_batch(self.h, pts.h, _ptr(pid), m, leaders.h, k, metric, _ptr(dist), _ptr(ids), _ptr(cnt)))
+        return dist, ids, cnt
 
     def kth_distance(self, pts, queries, k, metric=L2):
         q = self._rows(queries, pts.d, "kth_distance queries")

@@ -150,6 +150,28 @@ int gpann_topk_sharded_device(gpann_ctx* ctx, const gpann_points* pts, const flo
  * [row_begin,row_end) are scanned; ids are id_base + row. */
 int gpann_topk_range(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* queries,
                      size_t nq, int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+/* ---- segmented exact scans: the batched forms of the callers either side of the big scans.  One launch
+ *      serves all (query, segment) pairs; exact distances in the reference's arithmetic order (CUDA cores).  Single-device
+ *      contexts only. -------------------------------------------------------------------------------------------------- */
+/* InvertedIndex::Query / QueryBucket (src/inverted_index.h:43-75) for a BATCH of queries.  Bucket b owns the scan positions
+ * [bucket_offsets[b], bucket_offsets[b+1]).  permutation == NULL: `pts` is the clustered copy (position = row, reported ids
+ * are positions).  permutation != NULL: `pts` holds the ORIGINAL rows and position i is row permutation[i]; candidates are
+ * still ranked by (distance, POSITION) -- the reference's tie-break, :49-51 -- and the reported ids are permutation[position]
+ * (:56-59).  probes: [nq, nprobe] bucket ids per query (negative = unused; a bucket listed twice is probed once).
+ * out_* as gpann_topk. */
+int gpann_ivf_topk(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, size_t num_buckets,
+                   const uint32_t* permutation, const float* queries, size_t nq, const int32_t* probes, int nprobe, int k,
+                   int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+/* ApproximateKNNGraphBuilder::CrunchBucket (src/knn_graph.h:165-185) for ALL buckets at once: bucket b holds the points
+ * bucket_members[bucket_offsets[b] .. bucket_offsets[b+1]); for every member position p the k nearest OTHER members of its
+ * bucket, ranked by (distance, global id), ascending: out_dist / out_id [total,k], out_count[p] = min(k, bucket size - 1). */
+int gpann_knn_buckets(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* bucket_offsets, const uint32_t* bucket_members,
+                      size_t num_buckets, int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+/* ClosestLeaders (src/defs.cpp:87-96) for every listed point at once (src/knn_graph.h:75-81; point_ids == NULL: all m =
+ * n points): the k nearest rows of `leaders`, ids = leader index.  out_dist / out_id [m,k]. */
+int gpann_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint32_t* point_ids, size_t m,
+                                const gpann_points* leaders, int k, int metric, float* out_dist, uint32_t* out_id,
+                                uint32_t* out_count);
 /* Merge `parts` key lists per query ([parts,nq,k], e.g. the all-gathered per-GPU candidates) into the k
  * smallest keys per query; writes distances/ids (either may be NULL) and/or merged keys. */
 int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k,

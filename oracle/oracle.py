@@ -45,6 +45,7 @@ class Oracle:
         lib.oracle_objective.argtypes = [_f, _sz, _sz, _f, _i32, C.c_int]
         lib.oracle_random_sample.argtypes = [_f, _sz, _sz, _sz, C.c_int, _i32, C.c_void_p]
         lib.oracle_ivf_query.argtypes = [_f, _sz, _i32, _u32, _f, C.c_int, _i32, _sz, C.c_int, _f, _u32, _u32]
+        lib.oracle_crunch_bucket.argtypes = [_f, _sz, _u32, _sz, C.c_int, C.c_int, _f, _u32, _u32]
 
     def distance(self, p, q, metric=L2):
         p, q = _f32(p), _f32(q)
@@ -125,6 +126,18 @@ class Oracle:
         return dist[:cnt[0]], ids[:cnt[0]]
 
 
+    def crunch_bucket(self, points, bucket, k, metric=L2):
+        """Per-member top-k inside one bucket (global ids); returns (dist [m,k], ids [m,k], count [m])."""
+        points = _f32(points)
+        bucket = np.ascontiguousarray(bucket, np.uint32)
+        m = len(bucket)
+        dist = np.full((m, k), np.inf, np.float32)
+        ids = np.full((m, k), 0xFFFFFFFF, np.uint32)
+        cnt = np.zeros(m, np.uint32)
+        self.lib.oracle_crunch_bucket(points, points.shape[1], bucket, m, k, metric, dist, ids, cnt)
+        return dist, ids, cnt
+
+
 def ref_path(metric=L2):
     return os.path.join(HERE, "_ref", "libgpann_ref.so" if metric == L2 else "libgpann_ref_mips.so")
 
@@ -154,6 +167,8 @@ class Ref:
         lib.ref_random_sample.argtypes = [_f, _sz, _sz, _sz, C.c_int, _f]
         lib.ref_closest_leaders.argtypes = [_f, _sz, _sz, _f, _sz, C.c_uint32, C.c_int, _f, _u32, _u32]
         lib.ref_ivf_query.argtypes = [_f, _sz, _sz, _i32, _u32, _sz, _f, C.c_int, _i32, _sz, _f, _u32, _u32]
+        if hasattr(lib, "ref_crunch_bucket"):
+            lib.ref_crunch_bucket.argtypes = [_f, _sz, _sz, _u32, _sz, C.c_int, _f, _u32, _u32]
         lib.ref_pointset_create.restype = C.c_void_p
         lib.ref_pointset_create.argtypes = [_f, _sz, _sz]
         lib.ref_pointset_free.argtypes = [C.c_void_p]
@@ -228,6 +243,16 @@ class Ref:
         self.lib.ref_closest_leaders(points, points.shape[0], points.shape[1], leaders, leaders.shape[0], my_id, k, dist,
                                      ids, cnt)
         return dist[:cnt[0]], ids[:cnt[0]]
+
+    def crunch_bucket(self, points, bucket, k):
+        points = _f32(points)
+        bucket = np.ascontiguousarray(bucket, np.uint32)
+        m = len(bucket)
+        dist = np.full((m, k), np.inf, np.float32)
+        ids = np.full((m, k), 0xFFFFFFFF, np.uint32)
+        cnt = np.zeros(m, np.uint32)
+        self.lib.ref_crunch_bucket(points, points.shape[0], points.shape[1], bucket, m, k, dist, ids, cnt)
+        return dist, ids, cnt
 
     def ivf_query(self, points, clusters, q, k, buckets):
         points, q = _f32(points), _f32(q)

@@ -18,6 +18,7 @@
 #include "recall.h"  // defines (non-inline) ComputeGroundTruth & co; pulls in defs.h, dist.h, topn.h
 #include "kmeans.h"
 #include "inverted_index.h"
+#include "knn_graph.h"
 
 static PointSet make_pointset(const float* x, size_t n, size_t d) {
     PointSet ps;
@@ -154,6 +155,24 @@ void ref_ivf_query(const float* points, size_t n, size_t d, const int32_t* clust
     for (size_t i = 0; i < r.size(); ++i) {
         out_dist[i] = r[i].first;
         out_id[i] = r[i].second;
+    }
+}
+
+// ApproximateKNNGraphBuilder::CrunchBucket (knn_graph.h:165-185): all pairs inside one bucket, per-member top-k of
+// (distance, global id); member j's list goes to out_*[j*k ..].
+void ref_crunch_bucket(const float* points, size_t n, size_t d, const uint32_t* bucket, size_t m, int k, float* out_dist,
+                       uint32_t* out_id, uint32_t* out_count) {
+    PointSet P = make_pointset(points, n, d);
+    ApproximateKNNGraphBuilder builder;
+    builder.quiet = true;
+    std::vector<uint32_t> b(bucket, bucket + m);
+    std::vector<NNVec> res = builder.CrunchBucket(P, b, k);
+    for (size_t j = 0; j < m; ++j) {
+        out_count[j] = (uint32_t) res[j].size();
+        for (size_t r = 0; r < res[j].size(); ++r) {
+            out_dist[j * k + r] = res[j][r].first;
+            out_id[j * k + r] = res[j][r].second;
+        }
     }
 }
 

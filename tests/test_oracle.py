@@ -133,3 +133,35 @@ def test_oracle_vs_compiled_reference(oracle, ref):
     kth = ref.convert_ground_truth(P, Q, 10, d1, i1)
     assert np.array_equal(kth, d1[:, -1])
     assert ref.recall(d1, kth, 10) == 1.0
+
+
+def test_crunch_bucket_matches_reference_golden(oracle):
+    """ApproximateKNNGraphBuilder::CrunchBucket (src/knn_graph.h:165-185): float data within 1e-5, byte-valued data bit-exact
+    including the (distance, global id) tie-break."""
+    g = golden("crunch_buckets")
+    k = int(g["k"])
+    for b in range(len(g["offsets"]) - 1):
+        lo, hi = int(g["offsets"][b]), int(g["offsets"][b + 1])
+        d, i, c = oracle.crunch_bucket(g["points"], g["members"][lo:hi], k)
+        assert np.array_equal(c, g["count"][lo:hi])
+        assert_topk_close(d, i, g["dist"][lo:hi], g["ids"][lo:hi])
+    g = golden("crunch_buckets_u8_ties")
+    k = int(g["k"])
+    for b in range(len(g["offsets"]) - 1):
+        lo, hi = int(g["offsets"][b]), int(g["offsets"][b + 1])
+        d, i, c = oracle.crunch_bucket(g["points"].astype(np.float32), g["members"][lo:hi], k)
+        assert_topk_exact(d, i, g["dist"][lo:hi], g["ids"][lo:hi], c, g["count"][lo:hi])
+
+
+def test_ivf_batch_golden_is_the_per_query_scan(oracle):
+    """The batched fixture is the reference's InvertedIndex::Query run per query: ties break on the POSITION in the
+    clustered copy, reported ids go through the permutation (src/inverted_index.h:43-60)."""
+    g = golden("ivf_batch")
+    perm, off = g["permutation"], g["offsets"].astype(np.int32)
+    clustered = g["points"][perm]
+    for q in range(len(g["queries"])):
+        b = [int(x) for x in g["probes"][q] if x >= 0]
+        d, i = oracle.ivf_query(clustered, off, perm, g["queries"][q], 10, b)
+        n = len(d)
+        assert np.array_equal(i, g["ids"][q, :n]) and np.array_equal(d, g["dist"][q, :n])
+        assert np.isinf(g["dist"][q, n:]).all()
