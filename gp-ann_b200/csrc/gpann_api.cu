@@ -969,8 +969,9 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
 }
 
 // sums [kc,d] (optionally normalised) and counts [kc] of the points assigned to each cluster, fixed order.
+// MIPS build: d_row_norm [n] = |x_i| scales every row by 1/|x_i| and d_norm_sums [kc] receives the per-cluster sums of |x_i|^2.
 int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* d_assign, size_t kc, int normalize,
-                        float* d_out, uint64_t* d_counts, cudaStream_t st) {
+                        float* d_out, uint64_t* d_counts, cudaStream_t st, const float* d_row_norm = nullptr, float* d_norm_sums = nullptr) {
     const size_t n = pts->n;
     const int d = (int) pts->d;
     if (n > 0x7FFFFFFFull) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: n must be below 2^31 per device");
@@ -998,7 +999,7 @@ int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* 
     launch_cluster_segments(d_counts, (int) kc, seg_begin, member_begin, st);
     GP_TRY(check_launch(ctx, "cluster_segments_kernel"));
     const size_t max_segs = n / kSegRows + kc + 1;
-    GP_TRY(reserve(ctx, ctx->segsums, max_segs * d * 4));
+    GP_TRY(reserve(ctx, ctx->segsums, max_segs * d * 4 + max_segs * 4));
     ReduceParams rp;
     rp.pts = rows_view(pts);
     rp.members = idx_out;
@@ -1006,9 +1007,11 @@ int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* 
     rp.member_begin = member_begin;
     rp.kc = (int) kc;
     rp.seg_sums = (float*) ctx->segsums.p;
+    rp.row_norm = d_row_norm;
+    rp.seg_norm_sums = d_row_norm && d_norm_sums ? rp.seg_sums + max_segs * d : nullptr;
     launch_cluster_reduce_segments(rp, (unsigned) max_segs, st);
-    GP_TRY(check_launch(ctx, "cluster_reduce_segments_kernel"));
-    launch_cluster_finalize(rp.seg_sums, seg_begin, d_counts, (int) kc, d, normalize, d_out, st);
+    GP_TRY(check_launch(ctx, "cluster_reduce_segments_kernel", rp.seg_norm_sums ? 2 : 1));
+    launch_cluster_finalize(rp.seg_sums, seg_begin, d_counts, (int) kc, d, normalize, d_out, rp.seg_norm_sums, d_norm_sums, st);
     return check_launch(ctx, "cluster_finalize_kernel");
 }
 
@@ -1403,14 +1406,16 @@ int sd_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centr
 
 // assignment + this shard's per-cluster coordinate sums and counts (no division)
 int kmeans_partial(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, int metric, int32_t* d_assign,
-                   const unsigned char* d_alive, float* d_sums, uint64_t* d_counts, cudaStream_t st) {
+                   const unsigned char* d_alive, float* d_sums, uint64_t* d_counts, cudaStream_t st, const float* d_row_norm = nullptr,
+                   float* d_norm_sums = nullptr) {
     if (pts->n == 0) {
         CU_TRY(ctx, cudaMemsetAsync(d_sums, 0, kc * pts->d * 4, st));
         CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, kc * 8, st));
+        if (d_norm_sums) CU_TRY(ctx, cudaMemsetAsync(d_norm_sums, 0, kc * 4, st));
         return 0;
     }
     GP_TRY(kmeans_assign_device(ctx, pts, d_centroids, kc, metric, d_assign, nullptr, d_alive, st));
-    return cluster_sums_device(ctx, pts, d_assign, kc, 0, d_sums, d_counts, st);
+    return cluster_sums_device(ctx, pts, d_assign, kc, 0, d_sums, d_counts, st, d_row_norm, d_norm_sums);
 }
 
 int sd_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const float* dev_centroids, size_t kc, int metric,
@@ -1430,30 +1435,31 @@ int sd_kmeans_partial_device(gpann_ctx* ctx, const gpann_points* pts, const floa
     return kmeans_partial(ctx, pts, dev_centroids, kc, metric, d_assign, nullptr, dev_out_sums, dev_out_counts, st);
 }
 
+int kmeans_rounds_device(gpann_ctx* ctx, const gpann_points* pts, float* d_cent, size_t kc, int rounds, int metric, int32_t* d_assign,
+                         unsigned char* d_alive, uint64_t* d_counts, cudaStream_t st);
+
+// One Lloyd round through host buffers: rows of empty clusters all-zero, nothing renumbered (the reference's host-side
+// RemoveEmptyClusters, src/kmeans.cpp:29-50, stays with the caller).  L2 and MIPS builds.
 int sd_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, int metric, int32_t* out_assign,
                    uint64_t* out_sizes) {
     if (!ctx) return GPANN_E_ARG;
     if (!pts || !centroids_inout || !out_sizes) return fail(ctx, GPANN_E_ARG, "kmeans_step: null argument");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
-    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(ctx, GPANN_E_ARG, "kmeans_step: bad metric");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     OrderScope order(ctx, st);
     const size_t n = pts->n, d = pts->d;
-    GP_TRY(reserve(ctx, ctx->cent, kc * d * 4));
-    GP_TRY(reserve(ctx, ctx->sums, kc * d * 4));
-    GP_TRY(reserve(ctx, ctx->counts, kc * 8));
+    GP_TRY(reserve(ctx, ctx->km_run_cent, kc * d * 4));
+    GP_TRY(reserve(ctx, ctx->km_run_counts, kc * 8 + 64));
+    GP_TRY(reserve(ctx, ctx->km_run_alive, kc));
     GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids_inout, kc * d * 4, cudaMemcpyHostToDevice, st));
-    if (n) {
-        GP_TRY(kmeans_assign_device(ctx, pts, (const float*) ctx->cent.p, kc, metric, (int32_t*) ctx->assign.p, nullptr, nullptr, st));
-        GP_TRY(cluster_sums_device(ctx, pts, (const int32_t*) ctx->assign.p, kc, 1, (float*) ctx->sums.p, (uint64_t*) ctx->counts.p, st));
-    } else {
-        CU_TRY(ctx, cudaMemsetAsync(ctx->sums.p, 0, kc * d * 4, st));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->counts.p, 0, kc * 8, st));
-    }
-    CU_TRY(ctx, cudaMemcpyAsync(centroids_inout, ctx->sums.p, kc * d * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(ctx, cudaMemcpyAsync(out_sizes, ctx->counts.p, kc * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->km_run_cent.p, centroids_inout, kc * d * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->km_run_alive.p, 1, kc, st));
+    GP_TRY(kmeans_rounds_device(ctx, pts, (float*) ctx->km_run_cent.p, kc, 1, metric, (int32_t*) ctx->assign.p,
+                                (unsigned char*) ctx->km_run_alive.p, (uint64_t*) ctx->km_run_counts.p, st));
+    CU_TRY(ctx, cudaMemcpyAsync(centroids_inout, ctx->km_run_cent.p, kc * d * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(out_sizes, ctx->km_run_counts.p, kc * 8, cudaMemcpyDeviceToHost, st));
     if (out_assign && n) CU_TRY(ctx, cudaMemcpyAsync(out_assign, ctx->assign.p, n * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     return 0;
@@ -1467,12 +1473,22 @@ int sd_kmeans_step(gpann_ctx* ctx, const gpann_points* pts, float* centroids_ino
 int kmeans_rounds_device(gpann_ctx* ctx, const gpann_points* pts, float* d_cent, size_t kc, int rounds, int metric, int32_t* d_assign,
                          unsigned char* d_alive, uint64_t* d_counts, cudaStream_t st) {
     const size_t d = pts->d;
-    GP_TRY(reserve(ctx, ctx->km_run_sums, kc * d * 4));
+    const bool mips = metric == GPANN_METRIC_MIPS;
+    GP_TRY(reserve(ctx, ctx->km_run_sums, kc * d * 4 + kc * 4));
     float* d_sums = (float*) ctx->km_run_sums.p;
+    float* d_norm_sums = mips ? d_sums + kc * d : nullptr;  // behind the sums: one all-reduce covers both
+    float* d_row_norm = nullptr;
+    if (mips && pts->n && rounds > 0) {  // vector_sqrt_norms, once per KMeans call (src/kmeans.cpp:233-236)
+        GP_TRY(reserve(ctx, ctx->km_run_norms, pts->n * 4));
+        d_row_norm = (float*) ctx->km_run_norms.p;
+        launch_row_norms(rows_view(pts), d_row_norm, blocks_for(ctx, pts->n), st);
+        GP_TRY(check_launch(ctx, "row_norms_kernel"));
+    }
     for (int r = 0; r < rounds; ++r) {
-        GP_TRY(kmeans_partial(ctx, pts, d_cent, kc, metric, d_assign, d_alive, d_sums, d_counts, st));
-        if (ctx->comm_size > 1) GP_TRY(comm_allreduce_kmeans(ctx, d_sums, kc * d, d_counts, kc, st));
-        launch_kmeans_update(d_cent, d_sums, d_counts, d_alive, (int) kc, (int) d, st);
+        GP_TRY(kmeans_partial(ctx, pts, d_cent, kc, metric, d_assign, d_alive, d_sums, d_counts, st, d_row_norm, d_norm_sums));
+        if (ctx->comm_size > 1) GP_TRY(comm_allreduce_kmeans(ctx, d_sums, kc * d + (mips ? kc : 0), d_counts, kc, st));
+        if (mips) launch_kmeans_update_ip(d_cent, d_sums, d_counts, d_norm_sums, d_alive, (int) kc, (int) d, st);
+        else launch_kmeans_update(d_cent, d_sums, d_counts, d_alive, (int) kc, (int) d, st);
         GP_TRY(check_launch(ctx, "kmeans_update_kernel"));
     }
     return 0;
@@ -1501,7 +1517,7 @@ int kmeans_run_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* cen
     if (pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "kmeans_run: point set does not belong to this context");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");  // src/kmeans.cpp:229-231
     if (rounds < 0) return fail(ctx, GPANN_E_ARG, "kmeans_run: rounds < 0");
-    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(ctx, GPANN_E_ARG, "kmeans_run: bad metric");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = pts->n, d = pts->d;
@@ -1554,7 +1570,7 @@ int sd_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_cen
     if (!pts || !dev_centroids_inout || !dev_alive_inout || !dev_out_counts) return fail(ctx, GPANN_E_ARG, "kmeans_run_device: null argument");
     if (pts->ctx != ctx) return fail(ctx, GPANN_E_ARG, "kmeans_run: point set does not belong to this context");
     if (kc < 1) return fail(ctx, GPANN_E_ARG, "KMeans #centroids < 1");
-    if (metric != GPANN_METRIC_L2) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(ctx, GPANN_E_ARG, "kmeans_run: bad metric");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t) stream;
     OrderScope order(ctx, st);

@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(256) cluster_reduce_segments_kernel(const Redu
         float acc = 0.f;
         if (j < d && slot < nslots) {
             for (uint64_t m = sb + slot; m < se; m += nslots) {
-                const char* row = p.pts.rows + (size_t) p.members[m] * p.pts.pitch;
-                acc += load1<STORAGE>(row, j);
+                const uint32_t r = p.members[m];
+                const char* row = p.pts.rows + (size_t) r * p.pts.pitch;
+                const float x = load1<STORAGE>(row, j);
+                acc += p.row_norm ? x * (1.0f / p.row_norm[r]) : x;  // MIPS: P_i[j] * multiplier (src/kmeans.cpp:96-99)
             }
         }
         s_part[threadIdx.x] = acc;
@@ -195,13 +197,23 @@ __global__ void __launch_bounds__(256) cluster_reduce_segments_vec4_kernel(const
         // two independent rows per iteration keep more loads in flight; the adds stay in row order
         for (; m + nslots < se; m += 2 * (uint64_t) nslots) {
             const uint32_t r0 = p.members[m], r1 = p.members[m + nslots];
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) r0 * p.pts.pitch) + j);
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) r1 * p.pts.pitch) + j);
+            float4 x0 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) r0 * p.pts.pitch) + j);
+            float4 x1 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) r1 * p.pts.pitch) + j);
+            if (p.row_norm) {
+                const float m0 = 1.0f / p.row_norm[r0], m1 = 1.0f / p.row_norm[r1];
+                x0.x *= m0; x0.y *= m0; x0.z *= m0; x0.w *= m0;
+                x1.x *= m1; x1.y *= m1; x1.z *= m1; x1.w *= m1;
+            }
             acc.x += x0.x; acc.y += x0.y; acc.z += x0.z; acc.w += x0.w;
             acc.x += x1.x; acc.y += x1.y; acc.z += x1.z; acc.w += x1.w;
         }
         if (m < se) {
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) p.members[m] * p.pts.pitch) + j);
+            const uint32_t r0 = p.members[m];
+            float4 x0 = __ldg(reinterpret_cast<const float4*>(p.pts.rows + (size_t) r0 * p.pts.pitch) + j);
+            if (p.row_norm) {
+                const float m0 = 1.0f / p.row_norm[r0];
+                x0.x *= m0; x0.y *= m0; x0.z *= m0; x0.w *= m0;
+            }
             acc.x += x0.x; acc.y += x0.y; acc.z += x0.z; acc.w += x0.w;
         }
     }
@@ -217,11 +229,83 @@ __global__ void __launch_bounds__(256) cluster_reduce_segments_vec4_kernel(const
     }
 }
 
+// MIPS build: sum of |x_i|^2 over a segment's members (norm_sums of src/kmeans.cpp:95), fixed-order tree per segment.
+__global__ void __launch_bounds__(256) segment_norm_sums_kernel(const ReduceParams p) {
+    __shared__ float s_red[256];
+    const uint32_t seg = blockIdx.x;
+    if (seg >= p.seg_begin[p.kc]) return;
+    int lo = 0, hi = p.kc;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.seg_begin[mid] <= seg) lo = mid; else hi = mid;
+    }
+    const uint64_t cb = p.member_begin[lo], ce = p.member_begin[lo + 1];
+    const uint64_t sb = cb + (uint64_t) (seg - p.seg_begin[lo]) * kSegRows;
+    const uint64_t se = min(ce, sb + kSegRows);
+    float acc = 0.f;
+    for (uint64_t m = sb + threadIdx.x; m < se; m += 256) {
+        const float nr = p.row_norm[p.members[m]];
+        acc += nr * nr;
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int) threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.seg_norm_sums[seg] = s_red[0];
+}
+
+// |x_i| = sqrt(vec_norm(P_i)) (src/kmeans.cpp:235, src/dist.cpp:54-58: sequential sum of squares), one thread per row
+template <int STORAGE>
+__global__ void row_norms_kernel(const RowsView v, float* out_norm) {
+    for (size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x; r < v.n; r += (size_t) gridDim.x * blockDim.x) {
+        const char* row = v.rows + r * v.pitch;
+        float acc = 0.f;
+        for (int j = 0; j < v.d; ++j) {
+            const float x = load1<STORAGE>(row, j);
+            acc = __fmaf_rn(x, x, acc);
+        }
+        out_norm[r] = sqrtf(acc);
+    }
+}
+
+// NormalizeCentroidsIP (src/kmeans.cpp:61-76): C = sums * sqrt((norm_sums / size) / |sums|^2); clusters without members
+// are removed in place as in kmeans_update_kernel.
+__global__ void kmeans_update_ip_kernel(float* centroids, const float* sums, const uint64_t* counts, const float* norm_sums,
+                                        unsigned char* alive, int kc, int d) {
+    __shared__ float s_red[128];
+    const int c = blockIdx.x;
+    const uint64_t cnt = counts[c];
+    const bool live = alive[c] != 0 && cnt != 0;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const float x = sums[(size_t) c * d + j];
+        acc += x * x;
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int) threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const float current = s_red[0];
+    const float desired = live ? norm_sums[c] / (float) cnt : 0.f;
+    const float mult = live ? sqrtf(desired / current) : 0.f;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) centroids[(size_t) c * d + j] = live ? sums[(size_t) c * d + j] * mult : 0.f;
+    if (threadIdx.x == 0 && !live) alive[c] = 0;
+}
+
 // Per cluster: add its segment sums in segment order; optionally divide by the member count
 // (NormalizeCentroidsL2, src/kmeans.cpp:104-114).  Empty clusters give all-zero rows.
 __global__ void cluster_finalize_kernel(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc,
-                                        int d, int normalize, float* out /*[kc,d]*/) {
+                                        int d, int normalize, float* out /*[kc,d]*/, const float* seg_norm_sums, float* out_norm_sums) {
     const int c = blockIdx.x;
+    if (seg_norm_sums && threadIdx.x == 0) {
+        float tot = 0.f;
+        for (uint32_t s = seg_begin[c]; s < seg_begin[c + 1]; ++s) tot += seg_norm_sums[s];
+        out_norm_sums[c] = tot;
+    }
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
         float tot = 0.f;
         for (uint32_t s = seg_begin[c]; s < seg_begin[c + 1]; ++s) tot += seg_sums[(size_t) s * d + j];
@@ -365,10 +449,20 @@ void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaSt
     else if (p.pts.storage == kF32) cluster_reduce_segments_kernel<kF32><<<grid, 256, 0, st>>>(p);
     else if (p.pts.storage == kU8) cluster_reduce_segments_kernel<kU8><<<grid, 256, 0, st>>>(p);
     else cluster_reduce_segments_kernel<kS8><<<grid, 256, 0, st>>>(p);
+    if (p.row_norm && p.seg_norm_sums) segment_norm_sums_kernel<<<grid, 256, 0, st>>>(p);
+}
+void launch_row_norms(const RowsView& pts, float* out_norm, int blocks, cudaStream_t st) {
+    if (pts.storage == kF32) row_norms_kernel<kF32><<<blocks, 256, 0, st>>>(pts, out_norm);
+    else if (pts.storage == kU8) row_norms_kernel<kU8><<<blocks, 256, 0, st>>>(pts, out_norm);
+    else row_norms_kernel<kS8><<<blocks, 256, 0, st>>>(pts, out_norm);
+}
+void launch_kmeans_update_ip(float* centroids, const float* sums, const uint64_t* counts, const float* norm_sums, unsigned char* alive, int kc,
+                             int d, cudaStream_t st) {
+    kmeans_update_ip_kernel<<<(unsigned) kc, 128, 0, st>>>(centroids, sums, counts, norm_sums, alive, kc, d);
 }
 void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d, int normalize,
-                             float* out, cudaStream_t st) {
-    cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(seg_sums, seg_begin, counts, kc, d, normalize, out);
+                             float* out, const float* seg_norm_sums, float* out_norm_sums, cudaStream_t st) {
+    cluster_finalize_kernel<<<(unsigned) kc, 128, 0, st>>>(seg_sums, seg_begin, counts, kc, d, normalize, out, seg_norm_sums, out_norm_sums);
 }
 void launch_kmeans_update(float* centroids, const float* sums, const uint64_t* counts, unsigned char* alive, int kc, int d, cudaStream_t st) {
     kmeans_update_kernel<<<(unsigned) kc, 128, 0, st>>>(centroids, sums, counts, alive, kc, d);

@@ -577,7 +577,7 @@ int mg_kmeans_step(gpann_ctx* root, const gpann_points* pts, float* centroids_in
     GP_TRY(check_group_points(root, pts, "kmeans_step"));
     if (!centroids_inout || !out_sizes) return fail(root, GPANN_E_ARG, "kmeans_step: null argument");
     if (kc < 1) return fail(root, GPANN_E_ARG, "KMeans #centroids < 1");
-    if (metric != GPANN_METRIC_L2) return fail(root, GPANN_E_UNSUPPORTED, "kmeans: only the L2 build is implemented");
+    if (metric != GPANN_METRIC_L2 && metric != GPANN_METRIC_MIPS) return fail(root, GPANN_E_ARG, "kmeans_step: bad metric");
     const size_t d = pts->d;
     std::vector<float> cent_in(centroids_inout, centroids_inout + kc * d);  // rank 0 overwrites the caller's buffer
     const int rc = run_all(root, [&](int r, gpann_ctx* c) {

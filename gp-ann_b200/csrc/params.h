@@ -113,6 +113,10 @@ struct ReduceParams {
     const uint64_t* member_begin;  // [kc+1]
     int kc;
     float* seg_sums;               // [total_segments, d]
+    // MIPS build (SumPointsInClustersIP, src/kmeans.cpp:87-101): every row is scaled by 1/|x| before it is added, and the
+    // squared norms are summed per cluster beside the coordinates
+    const float* row_norm;         // optional [n]: |x_i| (vector_sqrt_norms of src/kmeans.cpp:235)
+    float* seg_norm_sums;          // optional [total_segments]: sum of |x_i|^2 over the segment
 };
 
 struct ObjectiveParams {
@@ -307,7 +311,11 @@ void launch_histogram_keys(const int32_t* assign, size_t n, int kc, unsigned lon
 void launch_cluster_segments(const uint64_t* counts, int kc, uint32_t* seg_begin, uint64_t* member_begin, cudaStream_t st);
 void launch_cluster_reduce_segments(const ReduceParams& p, unsigned grid, cudaStream_t st);
 void launch_cluster_finalize(const float* seg_sums, const uint32_t* seg_begin, const uint64_t* counts, int kc, int d,
-                             int normalize, float* out, cudaStream_t st);
+                             int normalize, float* out, const float* seg_norm_sums, float* out_norm_sums, cudaStream_t st);
+// MIPS k-means: |x_i| per row; centroid update of NormalizeCentroidsIP (src/kmeans.cpp:61-76)
+void launch_row_norms(const RowsView& pts, float* out_norm, int blocks, cudaStream_t st);
+void launch_kmeans_update_ip(float* centroids, const float* sums, const uint64_t* counts, const float* norm_sums, unsigned char* alive, int kc,
+                             int d, cudaStream_t st);
 void launch_objective(const ObjectiveParams& p, unsigned grid, size_t smem, double* d_out, cudaStream_t st);
 // gpann_kmeans_run (device-resident Lloyd rounds): centroid update with removed-cluster tracking, final compaction
 void launch_kmeans_update(float* centroids, const float* sums, const uint64_t* counts, unsigned char* alive, int kc, int d, cudaStream_t st);

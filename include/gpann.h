@@ -181,7 +181,9 @@ uint64_t gpann_pack_key(float dist, uint32_t id);
 void gpann_unpack_key(uint64_t key, float* dist, uint32_t* id);
 
 /* ---- k-means: replaces NearestCenters / AggregateClusters* / KMeans / ObjectiveValue
- *      (src/kmeans.cpp:12-27, 116-204, 228-244, 246-249).  L2 build only. --------------------------------- */
+ *      (src/kmeans.cpp:12-27, 116-204, 228-244, 246-249), L2 build and -DMIPS_DISTANCE build (metric = GPANN_METRIC_MIPS:
+ *      rows scaled by 1/|x| before they are summed, NormalizeCentroidsIP; src/kmeans.cpp:61-101).  The tcgen05 assignment
+ *      kernel serves L2; MIPS assignments run on the exact CUDA-core kernel. ------------------------------------------- */
 /* argmin over centroids with strict '<' (lowest index wins ties); out_mindist may be NULL. */
 int gpann_kmeans_assign(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int metric,
                         int32_t* out_assign, float* out_mindist);

@@ -164,3 +164,27 @@ def test_tensor_step_matches_cuda_core_step(ctx, gpann_mod, oracle):
     assert np.array_equal(c1.view(np.uint32), c0.view(np.uint32))  # same assignment -> same fixed-order sums
     a_or, _ = oracle.nearest_centers(P, C)
     assert np.array_equal(a1, a_or)
+
+
+def test_kmeans_mips_build_golden(ctx, gpann_mod, oracle):
+    """KMeans of the -DMIPS_DISTANCE build (src/kmeans.cpp:61-101: rows scaled by 1/|x|, NormalizeCentroidsIP): one call on the
+    GPU against the reference's 20 rounds.  The reference's inner product is compiled with -ffast-math (vectorised sum), so a
+    handful of near-tie points may flip; SURVEY 8c (iii): same survivors, objective within 1e-4."""
+    g = golden("kmeans_mips_d48_k16")
+    pts = ctx.upload(g["points"], storage=gpann_mod.STORAGE_F32)
+    assign, cent, sizes = ctx.kmeans_run(pts, g["init"], rounds=20, metric=gpann_mod.MIPS)
+    assert cent.shape == g["centroids"].shape
+    assert (assign == g["assign"]).mean() > 0.995
+    np.testing.assert_allclose(cent, g["centroids"], rtol=2e-3, atol=2e-3)
+    obj = ctx.objective(pts, cent, assign, metric=gpann_mod.MIPS)
+    assert abs(obj - float(g["objective"])) <= 1e-4 * abs(float(g["objective"]))
+    # one round through the host-buffer step: the assignment is the oracle's MIPS NearestCenters (sequential-FMA inner product)
+    a1, c1, s1 = ctx.kmeans_step(pts, g["init"], metric=gpann_mod.MIPS)
+    a0, _ = oracle.nearest_centers(g["points"], g["init"], metric=1)
+    assert np.array_equal(a1, a0)
+    assert int(s1.sum()) == len(g["points"]) and (np.bincount(a1, minlength=len(s1)) == s1).all()
+    # NormalizeCentroidsIP: |c|^2 = mean of the members' |x|^2 (src/kmeans.cpp:61-76)
+    P = g["points"].astype(np.float64)
+    for c in np.nonzero(s1)[0][:5]:
+        want = (P[a1 == c] ** 2).sum(1).mean()
+        assert abs((c1[c].astype(np.float64) ** 2).sum() - want) <= 1e-4 * want
