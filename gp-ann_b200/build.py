@@ -67,7 +67,7 @@ def build_dropin(force=False):
     sa = os.path.join(cxx, "standalone")
     out = os.path.join(HERE, "libgpann_dropin.so")
     srcs = [os.path.join(cxx, "dropin_shim.cpp"), os.path.join(cxx, "kmeans_gpu.cpp"), os.path.join(sa, "dist.cpp"),
-            os.path.join(sa, "defs.cpp")]
+            os.path.join(sa, "defs.cpp"), os.path.join(sa, "points_io.cpp")]
     deps = srcs + [os.path.join(cxx, f) for f in os.listdir(cxx)] + [os.path.join(sa, f) for f in os.listdir(sa)] + [OUT]
     if force or _stale(out, deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-I" + cxx, "-I" + sa, "-o", out, *srcs,

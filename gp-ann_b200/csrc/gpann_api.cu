@@ -231,6 +231,7 @@ struct TcPlan {
     const int* gate = nullptr;  // device flag the batch's kernels are gated on (byte storage: queries integer-valued)
     uint32_t* bound = nullptr;  // [nq_pad] per-query bounds of this batch: ctx->bound, or the peer-shared array of a sharded call
     bool peers = false;         // the kernels also push tightened bounds to the other ranks' arrays
+    int mips = 0;               // metric of the scan
     CUtensorMap tmap_q;
 };
 
@@ -275,8 +276,10 @@ void tc_plan_shape(TcPlan& pl, int storage, int d, int dp, size_t nqb, int k) {
     pl.gate = nullptr;
 }
 
-int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, const float* dq, size_t nqb, int k, cudaStream_t st) {
+int tc_prepare_queries(gpann_ctx* ctx, TcPlan& pl, int storage, int d, int dp, const float* dq, size_t nqb, int k, cudaStream_t st,
+                       int metric = GPANN_METRIC_L2) {
     tc_plan_shape(pl, storage, d, dp, nqb, k);
+    pl.mips = metric == GPANN_METRIC_MIPS;
     const size_t qrow_bytes = pl.is_float ? (size_t) dp * 2 : tc::kRowBytes;
     GP_TRY(reserve(ctx, ctx->qrows, pl.nq_pad * qrow_bytes));
     GP_TRY(reserve(ctx, ctx->qnorm, pl.nq_pad * 4));
@@ -351,6 +354,7 @@ int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L)
     a.id_base = lay.id_base;
     a.eps = 0.0078125f + 0.00006103515625f;  // 2^-7 (bf16 rounding of both operands) + 2^-14 (fp32 accumulation, K <= 128)
     a.gate = pl.gate;
+    a.mips = pl.mips;
     L.grid = (unsigned) (pl.G * L.S);
     L.smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
     return 0;
@@ -492,8 +496,8 @@ TcLayout layout_of(const gpann_points* pts) {
 // were gated on (nullptr for float storage): the caller queues the exact float scan behind, gated the other way.
 // `between` (optional) runs between the sample passes and the main pass of every batch: the sharded entry points
 // all-reduce the per-query bounds across their ranks there.
-int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, const TopkOut& out, cudaStream_t st,
-                const int** gate, const BetweenFn& between) {
+int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t nq, int k, int metric, const TopkOut& out,
+                cudaStream_t st, const int** gate, const BetweenFn& between) {
     const bool is_float = pts->storage == GPANN_STORAGE_F32;
     const int d = (int) pts->d;
     const size_t batch_max = tc_batch_max(ctx, is_float ? pts->dp / 64 : 1);
@@ -501,7 +505,7 @@ int topk_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* dq, size_t
     *gate = nullptr;
     for (size_t q0 = 0; q0 < nq; q0 += batch_max) {
         TcPlan pl;
-        GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st));
+        GP_TRY(tc_prepare_queries(ctx, pl, pts->storage, d, pts->dp, dq + q0 * d, std::min(batch_max, nq - q0), k, st, metric));
         *gate = pl.gate;
         GP_TRY(tc_sample(ctx, pl, lay, st));
         if (between) GP_TRY(between(pl.bound, pl.nqb, st));  // real queries only: the count every rank agrees on
@@ -697,7 +701,10 @@ int topk_stream_host_api(gpann_ctx* ctx, const void* host_rows, int host_kind, i
 // issue the same sequence of collectives (multi.cu).
 bool tensor_shape(const gpann_ctx* ctx, int storage, size_t d, size_t nq, int k, int metric, bool full) {
     const bool is_float = storage == GPANN_STORAGE_F32;
-    if (metric != GPANN_METRIC_L2 || !full || k > 448 || d > (size_t) (is_float ? 64 * tc::kMaxKBlocks : tc::kRowBytes)) return false;
+    // both metrics: 1 - <q,x> is the same contraction without the norms (byte data: exact integers; float data: bf16 filter
+    // with the error bound eps*|q|*|x| + exact sequential-FMA re-rank)
+    (void) metric;
+    if (!full || k > 448 || d > (size_t) (is_float ? 64 * tc::kMaxKBlocks : tc::kRowBytes)) return false;
     return ctx->algo == GPANN_ALGO_TENSOR || (ctx->algo == GPANN_ALGO_AUTO && nq > 16);
 }
 int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
@@ -716,10 +723,10 @@ int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, siz
         GP_TRY(build_tensor_float(ctx, const_cast<gpann_points*>(pts), st));
     const bool tensor_ok = want_tensor && pts->has_tensor;
     if (ctx->algo == GPANN_ALGO_TENSOR && !tensor_ok)
-        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs d<=128, L2, full range, k<=448");
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs d<=128, full range, k<=448");
     const int* gate = nullptr;
     if (tensor_ok) {
-        GP_TRY(topk_tensor(ctx, pts, dq, nq, k, out, st, &gate, between));
+        GP_TRY(topk_tensor(ctx, pts, dq, nq, k, metric, out, st, &gate, between));
         if (!gate) return 0;
         ctx->gate_used = true;  // float storage: nothing can refute the tensor path
         // byte storage: the exact float scan is queued behind, gated on "queries were NOT integer-valued" -- normally every

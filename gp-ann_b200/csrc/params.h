@@ -211,6 +211,7 @@ struct Args {
     uint32_t* pace;          // optional [S*G] tile positions of the CTAs (zeroed before the launch): L2 pacing of a split's CTAs
     unsigned long long* stats;  // optional diagnostics (GPANN_TC_STATS): [0] records pushed, [1] slow-path entries
     const int* gate;         // optional device flag (queries are integer-valued): the kernel returns at once when *gate == 0
+    int mips;                // 1: MIPS build of the scan (distance = 1 - <q,x>, src/dist.cpp:50-52); 0: squared L2
     uint32_t* peer_bound[kMaxPeers];  // sharded calls: the other ranks' `bound` arrays (NVLink peer memory), same slot layout
     int npeers;
 };

@@ -46,14 +46,8 @@
 #ifndef GPANN_DRAIN_ALL
 #define GPANN_DRAIN_ALL 0
 #endif
-// 1: software-pipelined filter loop (one chunk pair of TMEM loads always in flight behind the max trees); 0: the plain loop.
-// Measured (round 2, profiles/r2_summary.md): SLOWER, 150 vs 96 ms at 100M -- with the next item's loads queued behind the
-// wait for ITS accumulator, every slow-path entry and both tree pairs sit between an accumulator's arrival and the release
-// of its slot, the MMA issuer starves (ncu: 52 % of the filter warps' samples on the accumulator wait) and the restructured
-// loop carries 244 instead of ~130 instructions per warp and item.  Kept as a build knob.
-#ifndef GPANN_PIPE
-#define GPANN_PIPE 0
-#endif
+// (A software-pipelined drain -- the next chunk pair's TMEM loads queued behind the current pair's max trees, across items --
+// was built and measured in round 2: 150 vs 96 ms at 100M, see profiles/r2_summary.md; commit 84d16f3 has the code.)
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
 #endif
@@ -138,7 +132,7 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
 // a chain of 32 compare+branch pairs costs a lone hit lane ~15 cycles per untaken branch (in-order issue), and every
 // cycle a filter warp loses here delays the whole TMEM pipeline, so the hits are collected into a bit mask first.
 __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, const int32_t* tn, const uint32_t* ti, int col0,
-                                              int nqv, uint32_t qs, const Queue& q) {
+                                              int nqv, uint32_t qs, const Queue& q, int mips) {
     uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -154,7 +148,7 @@ __device__ __forceinline__ void enqueue_chunk(const uint32_t (&v)[32], int T, co
         const uint32_t id = ti[col0 + j];
         if (id != kInvalidId) {
             const int acc = (int) pick32(v, j);
-            const int dist = nqv + tn[col0 + j] - 2 * acc;
+            const int dist = mips ? 1 - acc : nqv + tn[col0 + j] - 2 * acc;  // MIPS build: 1 - <q,x> (src/dist.cpp:50-52)
             queue_push(q, pack_key((float) dist, id), qs);
         }
     }
@@ -182,49 +176,6 @@ __device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T
     }
 }
 
-// Out-of-line slow path of the PIPELINED filter loop (GPANN_PIPE): the 64 values of a chunk pair sit in the lane's local
-// memory (copied there only when some lane of the warp saw a value reach its threshold), so the hot loop carries one call
-// instead of two inlined select trees per pair and stays small.  Ta / Tb: thresholds of the two 32-column chunks (a chunk
-// whose maximum did not reach the threshold gets "never").  Same records as enqueue_chunk / enqueue_chunk_f.
-template <bool kFloat>
-__device__ __noinline__ void slow_pair(const uint32_t* v, uint32_t Ta_bits, uint32_t Tb_bits, const int32_t* tn, const uint32_t* ti,
-                                       int col0, int nqv, uint32_t qs, uint32_t* q_tail, volatile uint32_t* q_head, uint4* q_rec,
-                                       uint32_t q_cap) {
-    Queue q;
-    q.cap = q_cap;
-    q.rec = q_rec;
-    q.tail = q_tail;
-    q.head = q_head;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t Tbits = half ? Tb_bits : Ta_bits;
-        const uint32_t* vv = v + 32 * half;
-        uint32_t mask = 0;
-        if (kFloat) {
-            const float T = __uint_as_float(Tbits);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(vv[j]) >= T) ? (1u << j) : 0u;
-        } else {
-            const int T = (int) Tbits;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= ((int) vv[j] >= T) ? (1u << j) : 0u;
-        }
-        const int c0 = col0 + 32 * half;
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t id = ti[c0 + j];
-            if (id == kInvalidId) continue;
-            if (kFloat) {
-                queue_push(q, ((uint64_t) vv[j] << 32) | id, qs, (uint32_t) tn[c0 + j]);
-            } else {
-                const int dist = nqv + tn[c0 + j] - 2 * (int) vv[j];
-                queue_push(q, pack_key((float) dist, id), qs);
-            }
-        }
-    }
-}
-
 // Per-query selection state owned by the selection warps (shared memory, indexed by query slot qs).
 struct SelState {
     uint64_t* kth;   // current k-th best key (kEmptyKey until k keys are held)
@@ -245,6 +196,7 @@ struct SelState {
     uint32_t* dirty;   // shared-memory bitmap [nslots/32]: bound tightened since the last push to the peers
     uint64_t* lists; // [nslots][stride] keys of this CTA: global (L2), or shared memory when k <= kSmemListKeys
     int k, cap, stride;
+    int mips;        // MIPS build: distance = 1 - <q,x>; the threshold source is U = 1 - kth instead of |q|^2 - kth
     // float path: exact re-rank inputs
     const float* rows_f32;  // [n, d]
     const float* q_f32;     // this CTA's queries [nslots, d]
@@ -299,11 +251,11 @@ __device__ __forceinline__ float exact_sqr_l2(const float* __restrict__ x, const
 // insert).  Larger k: append; the caller compacts a full list warp-wide.  Returns true if the list needs compaction.
 template <bool kFloat>
 __device__ __forceinline__ void apply_bound(const SelState& s, uint32_t qs, float kth_dist) {
-    if (kFloat) {  // U = |q|^2 - kth (float bits in the int arrays); monotone non-decreasing
-        const float u = __int_as_float(s.nq[qs]) - kth_dist;
+    if (kFloat) {  // U = |q|^2 - kth (MIPS: 1 - kth), float bits in the int arrays; monotone non-decreasing
+        const float u = (s.mips ? 1.f : __int_as_float(s.nq[qs])) - kth_dist;
         s.U[qs] = __float_as_int(fmaxf(__int_as_float(s.U[qs]), u));
     } else {
-        s.U[qs] = max(s.U[qs], s.nq[qs] - (int) kth_dist);
+        s.U[qs] = max(s.U[qs], (s.mips ? 1 : s.nq[qs]) - (int) kth_dist);
     }
 }
 template <bool kFloat>
@@ -342,13 +294,22 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         const uint64_t kth_now = s.kth[qs];
         if (kth_now != kEmptyKey) {  // same test as the filter's, with this point's own norm and the current k-th distance
             const float nqv = __int_as_float(s.nq[qs]), nx = __uint_as_float(extra), acc = __uint_as_float((uint32_t) (key >> 32));
-            const float lb = nqv + nx - 2.f * acc - (2.f * s.eps * sqrtf(nqv * nx) + 1e-5f * (nqv + nx));
+            const float lb = s.mips ? 1.f - acc - (s.eps * sqrtf(nqv * nx) + 1e-5f * (1.f + fabsf(acc)))
+                                    : nqv + nx - 2.f * acc - (2.f * s.eps * sqrtf(nqv * nx) + 1e-5f * (nqv + nx));
             if (lb - 1e-6f * fabsf(lb) > key_dist(kth_now)) return false;
         }
         const float* xrow = s.rows_f32 + (size_t) (id - s.id_base) * s.d;
         // the row is a random 4*d bytes of HBM: request all of its lines at once instead of one miss per loop trip
         for (int off = 128; off < s.d * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xrow) + off));
-        const float dist = exact_sqr_l2(xrow, s.q_f32 + (size_t) qs * s.d, s.d);
+        float dist;
+        if (s.mips) {  // inner_product (src/dist.cpp:42-48): sequential FMA; mips_distance = 1 - <p,q>
+            const float* qrow = s.q_f32 + (size_t) qs * s.d;
+            float r = 0.f;
+            for (int i = 0; i < s.d; ++i) r = __fmaf_rn(qrow[i], xrow[i], r);
+            dist = __fsub_rn(1.0f, r);
+        } else {
+            dist = exact_sqr_l2(xrow, s.q_f32 + (size_t) qs * s.d, s.d);
+        }
         key = pack_key(dist, id);
     }
     uint64_t* list = s.lists + (size_t) qs * s.stride;
@@ -544,11 +505,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         if (kFloat) {
             const float nqv = reinterpret_cast<const float*>(a.qnorm)[qbase + i];
             s_nq[i] = __float_as_int(nqv);
-            s_U[i] = __float_as_int(padding ? 3.0e38f : (b < 3.0e38f) ? nqv - b : -3.0e38f);
+            s_U[i] = __float_as_int(padding ? 3.0e38f : (b < 3.0e38f) ? (a.mips ? 1.f : nqv) - b : -3.0e38f);
         } else {
             const int nqv = reinterpret_cast<const int32_t*>(a.qnorm)[qbase + i];
             s_nq[i] = nqv;
-            s_U[i] = padding ? (1 << 29) : (b < 3.0e9f) ? nqv - (int) b : -(1 << 30);
+            s_U[i] = padding ? (1 << 29) : (b < 3.0e9f) ? (a.mips ? 1 : nqv) - (int) b : -(1 << 30);
         }
     }
     for (int i = tid; i < kSelWarps * a.qcap; i += kThreads) s_qrec[i] = make_uint4(0u, 0u, kQEmpty, 0u);
@@ -813,151 +774,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const uint32_t tbase0 = tmem_base + col_base + lane_sel;
         const int sample_pass = a.sample_pass;
         const float eps = a.eps;
-#if GPANN_PIPE
-        // ===== software-pipelined drain (production path) =====
-        // A filter warp owns 128 columns of every item = two chunk pairs (2 x tcgen05.ld.x32 each).  The loads of the NEXT
-        // pair -- the second pair of this item, or the first pair of the next item -- are issued right after the wait for the
-        // current pair and before its max trees, so one pair is always in flight behind the ALU work (the plain loop exposes
-        // the ~150 clk TMEM round trip twice per item: 650-700 clk per item against 512 clk of MMA).  128 data registers.
-        constexpr bool kPipe = !kFilterByItem && kHalves == 1 && kColsPerWarp == 128 && kSlots == 2 && !GPANN_DRAIN_ALL;
-        if (kPipe && mode == 0 && tile_begin < tile_end) {
-            const uint32_t nitems = (tile_end - tile_begin) * (uint32_t) R;
-            uint32_t pa0[32], pa1[32], pb0[32], pb1[32];
-            int r = 0;
-            bool first_of_tile = true;
-            // prologue: item 0, pair 0
-            mbar_wait(bar_tfull, 0);
-            tcgen05_fence_after();
-            tmem_ld32(tbase0, pa0);
-            tmem_ld32(tbase0 + 32, pa1);
-            const int32_t* tn = s_norm;
-            const uint32_t* ti = s_id;
-            int nmin_i = 0;
-            float nmin_f = 0.f, nmax_f = 0.f, rmin_f = 0.f, rmax_f = 0.f;
-            for (uint32_t it = 0; it < nitems; ++it) {
-                const uint32_t bar_te = bar_tempty + 8 * slot;
-                const uint32_t tbase = tbase0 + slot * kAccN;
-                tmem_wait_ld();                       // pair 0 of this item is in registers
-                tmem_ld32(tbase + 64, pb0);           // pair 1 in flight behind pair 0's trees
-                tmem_ld32(tbase + 96, pb1);
-                if (first_of_tile) {                  // the tile's norms / ids arrived with its operands (normally immediate)
-                    const long long c0 = stats ? clock64() : 0;
-                    mbar_wait(bar_full + 8 * st, ph);
-                    if (stats) w_pfull += clock64() - c0;
-                    tn = s_norm + st * kTileN;
-                    ti = s_id + st * kTileN;
-                    nmin_i = tn[0];
-                    if (kFloat) {
-                        nmin_f = __int_as_float(tn[0]);
-                        nmax_f = __int_as_float(tn[kAccN - 1]);
-                        rmin_f = sqrtf(nmin_f);
-                        rmax_f = sqrtf(nmax_f);
-                    }
-                }
-                const uint32_t qs = (uint32_t) (r * kTileM + qrow);
-                const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
-                const int nqraw = s_nq[qs];
-                int Ti = 0;
-                float Tf = 0.f;
-                if (kFloat) {  // see the plain loop below for the derivation
-                    const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
-                    const float sq = 2.f * eps * sqrtf(nqv);
-                    const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
-                    const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
-                    float gmin = fminf(g0, g1);
-                    const float nstar = eps * eps * nqv;
-                    if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
-                    Tf = 0.5f * (U + gmin);
-                    Tf -= 1e-6f * fabsf(Tf);
-                } else {
-                    Ti = (Uraw + nmin_i + 1) >> 1;
-                }
-                const bool cold = sample_pass && (kFloat ? Tf < -1.0e37f : Ti < -(1 << 28));
-                // ---- trees of pair 0 (columns col_base + [0,64)) ----
-                {
-                    bool hit;
-                    uint32_t Ta, Tb;
-                    if (kFloat) {
-                        const float ma = max32f(pa0), mb = max32f(pa1);
-                        hit = fmaxf(ma, mb) >= Tf;
-                        Ta = __float_as_uint(ma >= Tf ? (cold ? ma : Tf) : 3.0e38f);
-                        Tb = __float_as_uint(mb >= Tf ? (cold ? mb : Tf) : 3.0e38f);
-                    } else {
-                        const int ma = max32(pa0), mb = max32(pa1);
-                        hit = max(ma, mb) >= Ti;
-                        Ta = (uint32_t) (ma >= Ti ? (cold ? ma : Ti) : 0x7fffffff);
-                        Tb = (uint32_t) (mb >= Ti ? (cold ? mb : Ti) : 0x7fffffff);
-                    }
-                    if (__any_sync(0xffffffffu, hit)) {
-                        ++slow_entries;
-                        if (hit) {
-                            uint32_t tmp[64];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) tmp[j] = pa0[j], tmp[32 + j] = pa1[j];
-                            slow_pair<kFloat>(tmp, Ta, Tb, tn, ti, col_base, nqraw, qs, q.tail, q.head, q.rec, q.cap);
-                        }
-                        __syncwarp();
-                    }
-                }
-                tmem_wait_ld();                       // pair 1 in registers: the accumulator is drained
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_te);   // slot back to the MMA issuer before the arithmetic
-                // advance to the next item and put ITS first pair in flight behind pair 1's trees
-                const bool last_of_tile = r + 1 == R;
-                if (++slot == (uint32_t) kSlots) {
-                    slot = 0;
-                    sph ^= 1;
-                }
-                if (it + 1 < nitems) {
-                    const long long c1 = stats ? clock64() : 0;
-                    mbar_wait(bar_tfull + 8 * slot, sph);
-                    if (stats) w_tfull += clock64() - c1;
-                    tcgen05_fence_after();
-                    tmem_ld32(tbase0 + slot * kAccN, pa0);
-                    tmem_ld32(tbase0 + slot * kAccN + 32, pa1);
-                }
-                // ---- trees of pair 1 (columns col_base + [64,128)) ----
-                {
-                    bool hit;
-                    uint32_t Ta, Tb;
-                    if (kFloat) {
-                        const float ma = max32f(pb0), mb = max32f(pb1);
-                        hit = fmaxf(ma, mb) >= Tf;
-                        Ta = __float_as_uint(ma >= Tf ? (cold ? ma : Tf) : 3.0e38f);
-                        Tb = __float_as_uint(mb >= Tf ? (cold ? mb : Tf) : 3.0e38f);
-                    } else {
-                        const int ma = max32(pb0), mb = max32(pb1);
-                        hit = max(ma, mb) >= Ti;
-                        Ta = (uint32_t) (ma >= Ti ? (cold ? ma : Ti) : 0x7fffffff);
-                        Tb = (uint32_t) (mb >= Ti ? (cold ? mb : Ti) : 0x7fffffff);
-                    }
-                    if (__any_sync(0xffffffffu, hit)) {
-                        ++slow_entries;
-                        if (hit) {
-                            uint32_t tmp[64];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) tmp[j] = pb0[j], tmp[32 + j] = pb1[j];
-                            slow_pair<kFloat>(tmp, Ta, Tb, tn, ti, col_base + 64, nqraw, qs, q.tail, q.head, q.rec, q.cap);
-                        }
-                        __syncwarp();
-                    }
-                }
-                first_of_tile = false;
-                ++r;
-                if (last_of_tile) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms / ids
-                    if (++st == (uint32_t) NST) {
-                        st = 0;
-                        ph ^= 1;
-                    }
-                    r = 0;
-                    first_of_tile = true;
-                }
-            }
-        } else
-#endif
+        const int mips = a.mips;
         for (uint32_t t = tile_begin; t < tile_end; ++t) {
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
             const long long c0 = stats ? clock64() : 0;
@@ -1007,9 +824,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                         const float nstar = eps * eps * nqv;
                         if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
                         Tf = 0.5f * (U + gmin);
+                        if (mips) {  // keep x if 1 - dot <= kth: dot~ >= U - eps*|q|*|x|, |x| <= the item's largest norm
+                            const float qx = sqrtf(nqv) * rmax_f;
+                            Tf = U - eps * qx - 1e-5f * (1.f + fabsf(U) + qx);
+                        }
                         Tf -= 1e-6f * fabsf(Tf);
                     } else {
-                        Ti = (Uraw + nmin_i[h] + 1) >> 1;
+                        Ti = mips ? Uraw : (Uraw + nmin_i[h] + 1) >> 1;  // MIPS: acc >= 1 - kth, exact in integers
                     }
                     if (mode == 5) continue;
                     const long long c1 = stats ? clock64() : 0;
@@ -1074,8 +895,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                             if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
                                 ++slow_entries;
                                 const bool cold = sample_pass && Ti < -(1 << 28);  // see the float branch
-                                if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col0, nqraw, qs, q);
-                                if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col0 + 32, nqraw, qs, q);
+                                if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col0, nqraw, qs, q, mips);
+                                if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col0 + 32, nqraw, qs, q, mips);
                                 __syncwarp();
                             }
                         }
@@ -1123,6 +944,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.d = a.d;
         ss.id_base = a.id_base;
         ss.eps = a.eps;
+        ss.mips = a.mips;
         ss.gbound = a.bound ? a.bound + qbase : nullptr;
         ss.npeers = a.bound ? a.npeers : 0;
         for (int pi = 0; pi < kMaxPeers; ++pi) ss.peer[pi] = pi < a.npeers ? a.peer_bound[pi] + qbase : nullptr;

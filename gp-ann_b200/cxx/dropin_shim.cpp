@@ -4,7 +4,9 @@
 #include <cstring>
 
 #include "recall.h"  // defines ComputeGroundTruth & co
+#include "ground_truth_file.h"
 #include "kmeans.h"
+#include "points_io.h"
 
 static PointSet make_pointset(const float* x, size_t n, size_t d) {
     PointSet ps;
@@ -96,4 +98,46 @@ void dropin_closest_leaders(const float* points, size_t np, size_t d, const floa
     }
 }
 
-}  // extern "C"
+
+// ComputeGroundTruthFromFile (bytes stay bytes) + WriteGroundTruth in the reference's file format; then read it back
+int dropin_ground_truth_file(const char* points_path, const float* queries, size_t nq, size_t d, int k, size_t chunk_rows, const char* gt_path,
+                             float* out_dist, uint32_t* out_id) {
+    try {
+        PointSet Q = make_pointset(queries, nq, d);
+        std::vector<NNVec> gt = ComputeGroundTruthFromFile(points_path, Q, k, chunk_rows);
+        WriteGroundTruth(gt_path, gt);
+        std::vector<NNVec> back = ReadGroundTruth(gt_path);
+        for (size_t q = 0; q < nq; ++q)
+            for (size_t r = 0; r < back[q].size(); ++r) {
+                out_dist[q * k + r] = back[q][r].first;
+                out_id[q * k + r] = back[q][r].second;
+            }
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << e.what() << std::endl;
+        return -1;
+    }
+}
+
+// host-only round trips of the file formats (no GPU): ReadPoints widens bytes like the reference's reader
+int dropin_read_points(const char* path, float* out, size_t cap, size_t* n, size_t* d) {
+    try {
+        PointSet P = ReadPoints(path);
+        *n = P.n;
+        *d = P.d;
+        if (P.coordinates.size() > cap) return -2;
+        std::memcpy(out, P.coordinates.data(), P.coordinates.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << e.what() << std::endl;
+        return -1;
+    }
+}
+int dropin_write_ground_truth(const char* path, const float* dist, const uint32_t* ids, size_t nq, size_t k) {
+    std::vector<NNVec> gt(nq, NNVec(k));
+    for (size_t q = 0; q < nq; ++q)
+        for (size_t r = 0; r < k; ++r) gt[q][r] = { dist[q * k + r], ids[q * k + r] };
+    WriteGroundTruth(path, gt);
+    return 0;
+}
+}

@@ -180,7 +180,7 @@ def test_edge_cases(ctx, gpann_mod, oracle):
         ctx.topk(pts, P[:2], 5, row_range=(10, 100))
     ctx.set_algo(gpann_mod.ALGO_TENSOR)
     with pytest.raises(gpann_mod.GpannError):
-        ctx.topk(pts, P[:2], 5, metric=gpann_mod.MIPS)  # the tensor kernels are L2-only: must refuse, not fall back
+        ctx.topk(pts, P[:2], 5, row_range=(0, 10))  # the tensor kernels scan whole sets: must refuse, not fall back
     d1, i1, c1 = ctx.topk(pts, P[:3], 5)  # tiny float set through the bf16 tensor path
     assert ctx.last_algo == "tensor_bf16"
     d0, i0, _ = oracle.ground_truth(P, P[:3], 5)
@@ -341,3 +341,35 @@ def test_stream_float_rows_holding_bytes_take_the_integer_kernel(ctx, oracle):
     assert ctx.last_algo == "tensor_bf16_stream"
     d0, i0, c0 = oracle.ground_truth(P, Q, 10)
     assert_topk_close(d1, i1, d0, i0)
+
+
+def test_mips_on_the_tensor_path(gpann_mod, oracle):
+    """The -DMIPS_DISTANCE build of the scan (distance = 1 - <q,x>, src/dist.cpp:50-52) on the tcgen05 kernels: exact integer
+    dot products for byte data (negative dots included), bf16 filter + sequential-FMA re-rank for float data."""
+    rng = np.random.default_rng(77)
+    with gpann_mod.Context(0) as c:
+        g = golden("gt_mips_d64_k5")
+        c.set_algo(gpann_mod.ALGO_TENSOR)
+        pts = c.upload(g["points"], storage=gpann_mod.STORAGE_F32)
+        d1, i1, c1 = c.topk(pts, g["queries"], 5, metric=gpann_mod.MIPS)
+        assert c.last_algo == "tensor_bf16"
+        assert_topk_close(d1, i1, g["dist"], g["ids"])
+        c.set_algo(gpann_mod.ALGO_AUTO)
+        for dtype, lo, hi in ((np.uint8, 0, 256), (np.int8, -128, 128)):
+            P = rng.integers(lo, hi, (150_000, 100)).astype(dtype)
+            Q = rng.integers(lo, hi, (200, 100)).astype(np.float32)
+            pb = c.upload_bytes(P)
+            d1, i1, _ = c.topk(pb, Q, 10, metric=gpann_mod.MIPS)
+            assert c.last_algo.startswith("tensor_")
+            pick = np.linspace(0, 199, 24).astype(int)
+            d0, i0, _ = oracle.ground_truth(P.astype(np.float32), Q[pick], 10, metric=1)
+            assert_topk_exact(d1[pick], i1[pick], d0, i0)
+            pb.free()
+        Pf = (rng.standard_normal((300_000, 96)) * rng.uniform(0.2, 3.0, (300_000, 1))).astype(np.float32)
+        Qf = rng.standard_normal((400, 96)).astype(np.float32)
+        pf = c.upload(Pf, storage=gpann_mod.STORAGE_F32)
+        d1, i1, _ = c.topk(pf, Qf, 20, metric=gpann_mod.MIPS)
+        assert c.last_algo == "tensor_bf16"
+        pick = np.linspace(0, 399, 32).astype(int)
+        d0, i0, _ = oracle.ground_truth(Pf, Qf[pick], 20, metric=1)
+        assert_topk_close(d1[pick], i1[pick], d0, i0, atol=1e-4)
