@@ -160,6 +160,12 @@ int gpann_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const u
     if (is_group(ctx)) return no_group(ctx, "closest_leaders_batch");
     return sd_closest_leaders_batch(ctx, pts, point_ids, m, leaders, k, metric, out_dist, out_id, out_count);
 }
+int gpann_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* group, int ngroups, const float* queries, size_t nq, int metric,
+                         float* out) {
+    if (!ctx) return GPANN_E_ARG;
+    if (is_group(ctx)) return no_group(ctx, "group_min_dist");
+    return sd_group_min_dist(ctx, pts, group, ngroups, queries, nq, metric, out);
+}
 int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k, float* dev_out_dist, uint32_t* dev_out_id,
                             uint64_t* dev_out_keys, void* stream) {
     if (!ctx) return GPANN_E_ARG;

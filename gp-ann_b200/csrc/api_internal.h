@@ -271,6 +271,8 @@ int sd_knn_buckets(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* buck
                    int k, int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
 int sd_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint32_t* point_ids, size_t m, const gpann_points* leaders, int k,
                              int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
+int sd_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* group, int ngroups, const float* queries, size_t nq, int metric,
+                      float* out);
 int sd_set_algo(gpann_ctx* ctx, int algo);
 int sd_set_timing(gpann_ctx* ctx, int on);
 float sd_last_kernel_ms(gpann_ctx* ctx);

@@ -85,6 +85,17 @@ struct SegMergeParams {
     uint32_t* out_count;
 };
 
+struct GroupMinParams {
+    const char* rows;        // scanned point set
+    size_t pitch, n;
+    int storage, d;
+    const int32_t* group;    // [n] group (shard / cluster) of every point, < 0 = ignored
+    int ngroups;
+    const float* queries;    // [nq, d]
+    int nq, qb, metric, spitch, qpitch, vec_ok;
+    uint32_t* out_ordered;   // [nq, ngroups] order-preserving uint32 images of the minima (initialised to "FLT_MAX")
+};
+
 // ---- kmeans.cu ----------------------------------------------------------------------------------------------
 struct RowsView {
     const char* rows;
@@ -300,6 +311,8 @@ cudaError_t stream_set_attributes();
 cudaError_t seg_set_attributes();
 void launch_seg_scan(const SegParams& p, unsigned grid, size_t smem, cudaStream_t st);
 void launch_seg_merge(const SegMergeParams& p, cudaStream_t st);
+void launch_group_min(const GroupMinParams& p, dim3 grid, size_t smem, cudaStream_t st);
+void launch_group_min_finish(uint32_t* ordered_inout_as_float, size_t count, int blocks, cudaStream_t st);
 cudaError_t kmeans_set_attributes();
 cudaError_t tc_set_attributes();
 

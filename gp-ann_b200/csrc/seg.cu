@@ -151,11 +151,80 @@ __global__ void __launch_bounds__(128) seg_merge_kernel(const SegMergeParams p) 
     if (lane == 0 && p.out_count) p.out_count[q] = valid;
 }
 
+// ---- per-group minimum distance ------------------------------------------------------------------------------------------
+// out[q][g] = min over the points of group g of distance(P_i, Q_q): BruteForceRouting (analyze_approximation_losses.cpp:42-56)
+// and the per-cluster ratings of the overlapping partitioner (src/overlapping_partitioning.cpp:170-179).  One thread per
+// point, query batches through shared memory, minima kept per CTA in shared memory as order-preserving uint32 images and
+// folded into the global table with atomicMin -- min is order-independent, so the result is deterministic.
+template <int STORAGE>
+__global__ void __launch_bounds__(kStreamTile) group_min_kernel(const GroupMinParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int elem = STORAGE == kF32 ? 4 : 1;
+    const int row_bytes = p.d * elem;
+    unsigned char* s_rows = smem_raw;
+    float* s_q = reinterpret_cast<float*>(s_rows + (size_t) kStreamTile * p.spitch);
+    uint32_t* s_min = reinterpret_cast<uint32_t*>(s_q + (size_t) p.qb * p.qpitch);  // [qb][ngroups]
+    const uint32_t kMax = float_to_ordered(3.402823466e+38f);
+    for (int q0 = blockIdx.y * p.qb; q0 < p.nq; q0 += gridDim.y * p.qb) {
+        const int nqb = min(p.qb, p.nq - q0);
+        __syncthreads();
+        for (int i = tid; i < nqb * p.d; i += kStreamTile) {
+            const int q = i / p.d, j = i - q * p.d;
+            s_q[q * p.qpitch + j] = p.queries[(size_t) (q0 + q) * p.d + j];
+        }
+        for (int i = tid; i < nqb * p.ngroups; i += kStreamTile) s_min[i] = kMax;
+        __syncthreads();
+        const size_t ntiles = (p.n + kStreamTile - 1) / kStreamTile;
+        for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const size_t r0 = tile * kStreamTile;
+            const int rows_here = (int) min((size_t) kStreamTile, p.n - r0);
+            const char* src = p.rows + r0 * p.pitch;
+            if (p.vec_ok) {
+                const int cpr = row_bytes >> 4;
+                for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
+                    const int r = idx / cpr, c = idx - r * cpr;
+                    *reinterpret_cast<int4*>(s_rows + (size_t) r * p.spitch + c * 16) =
+                        __ldg(reinterpret_cast<const int4*>(src + (size_t) r * p.pitch) + c);
+                }
+            } else {
+                for (int idx = tid; idx < rows_here * row_bytes; idx += kStreamTile) {
+                    const int r = idx / row_bytes, c = idx - r * row_bytes;
+                    s_rows[(size_t) r * p.spitch + c] = (unsigned char) src[(size_t) r * p.pitch + c];
+                }
+            }
+            __syncthreads();
+            if (tid < rows_here) {
+                const int g = p.group[r0 + tid];
+                if (g >= 0 && g < p.ngroups) {
+                    const char* myrow = reinterpret_cast<const char*>(s_rows) + (size_t) tid * p.spitch;
+                    for (int q = 0; q < nqb; ++q) {
+                        const float dist = ref_distance<STORAGE>(myrow, s_q + q * p.qpitch, p.d, p.metric);
+                        const uint32_t o = float_to_ordered(dist);
+                        if (o < s_min[q * p.ngroups + g]) atomicMin(&s_min[q * p.ngroups + g], o);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < nqb * p.ngroups; i += kStreamTile)
+            if (s_min[i] != kMax) atomicMin(p.out_ordered + (size_t) q0 * p.ngroups + i, s_min[i]);
+    }
+}
+
+__global__ void group_min_finish_kernel(uint32_t* x, size_t count) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t) gridDim.x * blockDim.x)
+        x[i] = __float_as_uint(ordered_to_float(x[i]));
+}
+
 cudaError_t seg_set_attributes() {
     const int big = 200 * 1024;
     cudaError_t e = cudaFuncSetAttribute(seg_scan_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(seg_scan_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(seg_scan_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(group_min_kernel<kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(group_min_kernel<kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(group_min_kernel<kS8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     return e;
 }
 
@@ -164,6 +233,13 @@ void launch_seg_scan(const SegParams& p, unsigned grid, size_t smem, cudaStream_
     else if (p.storage == kU8) seg_scan_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
     else seg_scan_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
 }
+
+void launch_group_min(const GroupMinParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    if (p.storage == kF32) group_min_kernel<kF32><<<grid, kStreamTile, smem, st>>>(p);
+    else if (p.storage == kU8) group_min_kernel<kU8><<<grid, kStreamTile, smem, st>>>(p);
+    else group_min_kernel<kS8><<<grid, kStreamTile, smem, st>>>(p);
+}
+void launch_group_min_finish(uint32_t* x, size_t count, int blocks, cudaStream_t st) { group_min_finish_kernel<<<blocks, 256, 0, st>>>(x, count); }
 
 void launch_seg_merge(const SegMergeParams& p, cudaStream_t st) {
     const size_t smem = (size_t) 4 * p.cap * sizeof(uint64_t);

@@ -262,4 +262,61 @@ int sd_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint
     return 0;
 }
 
+int sd_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* group, int ngroups, const float* queries, size_t nq, int metric,
+                      float* out) {
+    GP_TRY(check_common(ctx, pts, 1, metric, "group_min_dist"));
+    if (!group || !queries || !out || ngroups < 1) return fail(ctx, GPANN_E_ARG, "group_min_dist: bad argument");
+    if (nq == 0) return 0;
+    if (ngroups > 12288) return fail(ctx, GPANN_E_UNSUPPORTED, "group_min_dist: at most 12288 groups (per-CTA table in shared memory)");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    OrderScope order(ctx, st);
+    const size_t n = pts->n, d = pts->d;
+    ScopedDev d_group, d_q, d_out;
+    CU_TRY(ctx, d_group.alloc(n * 4));
+    CU_TRY(ctx, d_q.alloc(nq * d * 4));
+    CU_TRY(ctx, d_out.alloc(nq * (size_t) ngroups * 4));
+    if (n) CU_TRY(ctx, cudaMemcpyAsync(d_group.p, group, n * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemcpyAsync(d_q.p, queries, nq * d * 4, cudaMemcpyHostToDevice, st));
+    // "no point in this group": the order-preserving image of FLT_MAX, as the reference's min_dist starts (FLT_MAX)
+    std::vector<uint32_t> init(nq * (size_t) ngroups, float_to_ordered(3.402823466e+38f));
+    CU_TRY(ctx, cudaMemcpyAsync(d_out.p, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
+    GroupMinParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.rows = (const char*) pts->rows;
+    p.pitch = pts->pitch;
+    p.n = n;
+    p.storage = pts->storage;
+    p.d = (int) d;
+    p.group = d_group.as<int32_t>();
+    p.ngroups = ngroups;
+    p.queries = d_q.as<float>();
+    p.nq = (int) nq;
+    p.metric = metric;
+    const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
+    const int row_bytes = p.d * elem;
+    p.spitch = odd16_pitch(row_bytes);
+    p.qpitch = (p.d + 3) & ~3;
+    p.vec_ok = ((uintptr_t) pts->rows % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
+    const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
+    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) ngroups * 4;
+    if (tile_bytes + per_q > 190 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "group_min_dist: d too large for the shared-memory tile");
+    p.qb = (int) std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nq, 16), (96 * 1024) / per_q));
+    const size_t smem = tile_bytes + (size_t) p.qb * per_q;
+    if (n) {
+        const size_t ntiles = (n + kStreamTile - 1) / kStreamTile;
+        const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+        const unsigned gy = (unsigned) std::min<size_t>((nq + p.qb - 1) / p.qb, 1024);
+        const unsigned gx = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, std::max<size_t>(1, (size_t) ctx->num_sms * occ / gy)));
+        launch_group_min(p, dim3(gx, gy), smem, st);
+        GP_TRY(check_launch(ctx, "group_min_kernel"));
+    }
+    launch_group_min_finish(d_out.as<uint32_t>(), nq * (size_t) ngroups, blocks_for(ctx, nq * (size_t) ngroups), st);
+    GP_TRY(check_launch(ctx, "group_min_finish_kernel"));
+    CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, nq * (size_t) ngroups * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->last_algo = "group_min";
+    return 0;
+}
+
 }  // namespace gpimpl

@@ -49,6 +49,7 @@ SYMBOLS = {
     "gpann_ivf_topk": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "gpann_knn_buckets": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     "gpann_closest_leaders_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _vp, _vp, _vp]),
+    "gpann_group_min_dist": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "gpann_merge_keys_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
     "gpann_pack_key": (_u64, [C.c_float, _u32]),
     "gpann_unpack_key": (None, [_u64, C.POINTER(C.c_float), C.POINTER(_u32)]),
@@ -297,6 +298,16 @@ class Context:
         dist, ids, cnt = np.empty((m, k), np.float32), np.empty((m, k), np.uint32), np.empty(m, np.uint32)
         self.check(self.lib.gpann_closest_leaders_batch(self.h, pts.h, _ptr(pid), m, leaders.h, k, metric, _ptr(dist), _ptr(ids), _ptr(cnt)))
         return dist, ids, cnt
+
+    def group_min_dist(self, pts, group, ngroups, queries, metric=L2):
+        """out[q, g] = min distance from query q to the points of group g (FLT_MAX for an empty group)."""
+        q = self._rows(queries, pts.d, "group_min_dist queries")
+        grp = np.ascontiguousarray(group, dtype=np.int32)
+        if grp.shape != (pts.n,):
+            raise GpannError(f"group_min_dist: expected {pts.n} group ids, got shape {grp.shape}")
+        out = np.empty((q.shape[0], ngroups), np.float32)
+        self.check(self.lib.gpann_group_min_dist(self.h, pts.h, _ptr(grp), int(ngroups), _ptr(q), q.shape[0], metric, _ptr(out)))
+        return out
 
     def kth_distance(self, pts, queries, k, metric=L2):
         q = self._rows(queries, pts.d, "kth_distance queries")

@@ -172,6 +172,11 @@ int gpann_knn_buckets(gpann_ctx* ctx, const gpann_points* pts, const uint64_t* b
 int gpann_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint32_t* point_ids, size_t m,
                                 const gpann_points* leaders, int k, int metric, float* out_dist, uint32_t* out_id,
                                 uint32_t* out_count);
+/* Per-group minimum distance: out[q*ngroups + g] = min over the points i with group[i] == g of distance(P_i, Q_q), FLT_MAX for
+ * a group without points.  BruteForceRouting (analyze_approximation_losses.cpp:42-56) and the per-cluster ratings of the
+ * overlapping partitioner (src/overlapping_partitioning.cpp:170-179).  group: host int32 [n] (negative = ignored). */
+int gpann_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* group, int ngroups, const float* queries, size_t nq,
+                         int metric, float* out);
 /* Merge `parts` key lists per query ([parts,nq,k], e.g. the all-gathered per-GPU candidates) into the k
  * smallest keys per query; writes distances/ids (either may be NULL) and/or merged keys. */
 int gpann_merge_keys_device(gpann_ctx* ctx, const uint64_t* dev_keys, size_t parts, size_t nq, int k,

@@ -104,7 +104,11 @@ def test_streaming_scan_batches_large_query_sets(ctx, gpann_mod, oracle):
     P = rng.standard_normal((60_000, 24)).astype(np.float32)
     Q = rng.standard_normal((9_000, 24)).astype(np.float32)
     pts = ctx.upload(P)
-    d1, i1, c1 = ctx.topk(pts, Q, 100, metric=gpann_mod.MIPS)  # MIPS: always the streaming kernel
+    ctx.set_algo(gpann_mod.ALGO_STREAM)
+    try:
+        d1, i1, c1 = ctx.topk(pts, Q, 100, metric=gpann_mod.MIPS)
+    finally:
+        ctx.set_algo(gpann_mod.ALGO_AUTO)
     assert ctx.last_algo == "stream"
     pick = np.linspace(0, len(Q) - 1, 40).astype(int)
     d0, i0, _ = oracle.ground_truth(P, Q[pick], 100, metric=1)

@@ -77,3 +77,21 @@ def test_closest_leaders_batch_golden(ctx, gpann_mod, oracle):
     d3, i3, _ = ctx.closest_leaders_batch(pts, leaders, 2, point_ids=sub, metric=gpann_mod.MIPS)
     d0, i0, _ = oracle.ground_truth(P[lead], P[sub], 2, metric=1)
     assert_topk_close(d3, i3, d0, i0)
+
+
+def test_group_min_dist_matches_a_per_group_scan(ctx, gpann_mod, oracle):
+    """BruteForceRouting (analyze_approximation_losses.cpp:42-56): per query the minimum distance to every shard's points."""
+    rng = np.random.default_rng(61)
+    n, d, shards = 30_000, 100, 13
+    P = rng.standard_normal((n, d)).astype(np.float32)
+    part = rng.integers(0, shards - 1, n).astype(np.int32)  # the last shard stays empty
+    Q = rng.standard_normal((37, d)).astype(np.float32)
+    pts = ctx.upload(P, storage=gpann_mod.STORAGE_F32)
+    out = ctx.group_min_dist(pts, part, shards, Q)
+    assert (out[:, shards - 1] == np.finfo(np.float32).max).all()
+    for g in range(shards - 1):
+        d0, _, _ = oracle.ground_truth(P[part == g], Q, 1)
+        np.testing.assert_allclose(out[:, g], d0[:, 0], rtol=1e-6)
+    # probe order = the reference's routing order
+    probes = np.argsort(out, axis=1, kind="stable")
+    assert (probes[:, -1] == shards - 1).all()
