@@ -16,7 +16,7 @@ TAG = os.environ.get("GPANN_BUILD_TAG", "")
 EXTRA = os.environ.get("GPANN_NVCC_EXTRA", "").split()
 OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 OUT = os.path.join(HERE, "libgpann_cuda" + ("_" + TAG if TAG else "") + ".so")
-SOURCES = ["gpann_api.cu", "abi.cu", "multi.cu", "seg.cu", "seg_api.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
+SOURCES = ["gpann_api.cu", "abi.cu", "multi.cu", "seg.cu", "seg_api.cu", "bkm.cu", "topk_tc.cu", "kmeans_tc.cu", "stream.cu", "kmeans.cu", "prep.cu"]
 HEADERS = ["common.cuh", "distance.cuh", "params.h", "tc_ptx.cuh", "api_internal.h", os.path.join("..", "..", "include", "gpann.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

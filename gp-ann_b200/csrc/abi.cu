@@ -208,6 +208,12 @@ int gpann_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_
     if (is_group(ctx)) return no_group(ctx, "kmeans_run_device");
     return sd_kmeans_run_device(ctx, pts, dev_centroids_inout, kc, rounds, metric, dev_out_assign, dev_alive_inout, dev_out_counts, stream);
 }
+int gpann_balanced_kmeans(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, size_t max_cluster_size, int metric,
+                          int32_t* out_assign, uint64_t* out_sizes, size_t* out_kc) {
+    if (!ctx) return GPANN_E_ARG;
+    if (is_group(ctx)) return no_group(ctx, "balanced_kmeans");
+    return sd_balanced_kmeans(ctx, pts, centroids_inout, kc, max_cluster_size, metric, out_assign, out_sizes, out_kc);
+}
 int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric, double* out) {
     if (!ctx) return GPANN_E_ARG;
     return is_group(ctx) ? mg_objective(ctx, pts, centroids, kc, assign, metric, out) : sd_objective(ctx, pts, centroids, kc, assign, metric, out);

@@ -225,6 +225,13 @@ int kmeans_rounds_device(gpann_ctx* ctx, const gpann_points* pts, float* d_cent,
 int kmeans_run_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, int rounds, int metric);
 int kmeans_run_fetch(gpann_ctx* ctx, const gpann_points* pts, float* centroids_out, size_t kc, int32_t* out_assign, uint64_t* out_sizes,
                      size_t* out_kc);
+int objective_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, const int32_t* d_assign, int metric,
+                     double** d_out_ptr, cudaStream_t st);
+RowsView rows_view(const gpann_points* pts);
+int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* d_assign, size_t kc, int normalize, float* d_out,
+                        uint64_t* d_counts, cudaStream_t st, const float* d_row_norm = nullptr, float* d_norm_sums = nullptr);
+int kmeans_compact_device(gpann_ctx* ctx, float* d_cent, size_t kc, size_t d, int32_t* d_assign, size_t n, const unsigned char* d_alive,
+                          uint64_t* d_counts, int* d_kc_out, cudaStream_t st);
 int objective_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign, int metric,
                       double** d_out_ptr);
 
@@ -273,6 +280,8 @@ int sd_closest_leaders_batch(gpann_ctx* ctx, const gpann_points* pts, const uint
                              int metric, float* out_dist, uint32_t* out_id, uint32_t* out_count);
 int sd_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* group, int ngroups, const float* queries, size_t nq, int metric,
                       float* out);
+int sd_balanced_kmeans(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, size_t max_cluster_size, int metric,
+                       int32_t* out_assign, uint64_t* out_sizes, size_t* out_kc);
 int sd_set_algo(gpann_ctx* ctx, int algo);
 int sd_set_timing(gpann_ctx* ctx, int on);
 float sd_last_kernel_ms(gpann_ctx* ctx);

@@ -64,4 +64,11 @@ __device__ __forceinline__ float ref_distance(const char* row, const float* q, i
     }
 }
 
+// The same arithmetic with element-wise loads: for rows / queries in global memory whose alignment is not known.
+template <int STORAGE>
+__device__ __forceinline__ float ref_distance_scalar(const char* row, const float* q, int d, int metric) {
+    if (metric == kL2) return sqr_l2_ref_order([row](int i) { return load1<STORAGE>(row, i); }, q, d);
+    return __fsub_rn(1.0f, inner_product_ref_order([row](int i) { return load1<STORAGE>(row, i); }, q, d));
+}
+
 }  // namespace gpann

@@ -978,7 +978,7 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
 // sums [kc,d] (optionally normalised) and counts [kc] of the points assigned to each cluster, fixed order.
 // MIPS build: d_row_norm [n] = |x_i| scales every row by 1/|x_i| and d_norm_sums [kc] receives the per-cluster sums of |x_i|^2.
 int cluster_sums_device(gpann_ctx* ctx, const gpann_points* pts, const int32_t* d_assign, size_t kc, int normalize,
-                        float* d_out, uint64_t* d_counts, cudaStream_t st, const float* d_row_norm = nullptr, float* d_norm_sums = nullptr) {
+                        float* d_out, uint64_t* d_counts, cudaStream_t st, const float* d_row_norm, float* d_norm_sums) {
     const size_t n = pts->n;
     const int d = (int) pts->d;
     if (n > 0x7FFFFFFFull) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: n must be below 2^31 per device");
@@ -1599,10 +1599,17 @@ int objective_enqueue(gpann_ctx* ctx, const gpann_points* pts, const float* cent
     GP_TRY(reserve(ctx, ctx->assign, std::max<size_t>(n, 1) * 4));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->cent.p, centroids, kc * d * 4, cudaMemcpyHostToDevice, st));
     if (n) CU_TRY(ctx, cudaMemcpyAsync(ctx->assign.p, assign, n * 4, cudaMemcpyHostToDevice, st));
+    return objective_device(ctx, pts, (const float*) ctx->cent.p, kc, (const int32_t*) ctx->assign.p, metric, d_out_ptr, st);
+}
+
+// device-pointer form (centroids [kc,d], assign [n] already on the device); uses ctx->misc for the per-CTA partial sums
+int objective_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_centroids, size_t kc, const int32_t* d_assign, int metric,
+                     double** d_out_ptr, cudaStream_t st) {
+    const size_t n = pts->n, d = pts->d;
     ObjectiveParams p;
     p.pts = rows_view(pts);
-    p.centroids = (const float*) ctx->cent.p;
-    p.assign = (const int32_t*) ctx->assign.p;
+    p.centroids = d_centroids;
+    p.assign = d_assign;
     p.kc = (int) kc;
     p.metric = metric;
     const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;

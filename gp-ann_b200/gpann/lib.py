@@ -58,6 +58,7 @@ SYMBOLS = {
     "gpann_kmeans_partial_device": (_i, [_vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "gpann_kmeans_run": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, C.POINTER(_sz)]),
     "gpann_kmeans_run_device": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
+    "gpann_balanced_kmeans": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp, _vp, C.POINTER(_sz)]),
     "gpann_objective": (_i, [_vp, _vp, _vp, _sz, _vp, _i, C.POINTER(C.c_double)]),
 }
 
@@ -349,6 +350,16 @@ class Context:
         kc = C.c_size_t(0)
         self.check(self.lib.gpann_kmeans_run(self.h, pts.h, _ptr(c), c.shape[0], int(rounds), metric, _ptr(assign), _ptr(sizes),
                                              C.byref(kc)))
+        return assign, np.ascontiguousarray(c[:kc.value]), sizes[:kc.value]
+
+    def balanced_kmeans(self, pts, centroids, max_cluster_size, metric=L2):
+        """BalancedKMeans (src/kmeans.cpp:251-524).  Returns (assignment, centroids, sizes) with every size <= max_cluster_size."""
+        c = self._rows(centroids, pts.d, "balanced_kmeans centroids").copy()
+        assign = np.empty(pts.n, np.int32)
+        sizes = np.empty(c.shape[0], np.uint64)
+        kc = C.c_size_t(0)
+        self.check(self.lib.gpann_balanced_kmeans(self.h, pts.h, _ptr(c), c.shape[0], int(max_cluster_size), metric, _ptr(assign), _ptr(sizes),
+                                                  C.byref(kc)))
         return assign, np.ascontiguousarray(c[:kc.value]), sizes[:kc.value]
 
     def kmeans_run_device(self, pts, dev_centroids, kc, rounds, dev_alive, dev_counts, dev_assign=None, metric=L2, stream=None):

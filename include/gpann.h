@@ -216,6 +216,13 @@ int gpann_kmeans_run(gpann_ctx* ctx, const gpann_points* pts, float* centroids_i
  * every rank passes its shard and all ranks end with identical centroids. */
 int gpann_kmeans_run_device(gpann_ctx* ctx, const gpann_points* pts, float* dev_centroids_inout, size_t kc, int rounds, int metric,
                             int32_t* dev_out_assign, unsigned char* dev_alive_inout, uint64_t* dev_out_counts, void* stream);
+/* BalancedKMeans (src/kmeans.cpp:251-524): KMeans, then rounds of 1000 mini-batches in which every point scores all clusters by
+ * pos_distance + round_penalty * cluster_size under the BKM+ admissibility rule, moves, and the centroids follow; the penalty
+ * rises until no cluster holds more than max_cluster_size points (at most 150 rounds, then the greedy re-migration of
+ * :493-517).  The reference's moving phase is a racy parallel_for, so neither side is reproducible bit for bit: parity is
+ * "balanced, and the objective within a few per cent".  Outputs as gpann_kmeans_run.  Single-device contexts. */
+int gpann_balanced_kmeans(gpann_ctx* ctx, const gpann_points* pts, float* centroids_inout, size_t kc, size_t max_cluster_size,
+                          int metric, int32_t* out_assign, uint64_t* out_sizes, size_t* out_kc);
 /* sum_i pos_distance(P_i, C_assign[i]) accumulated in double (src/kmeans.cpp:246-249). */
 int gpann_objective(gpann_ctx* ctx, const gpann_points* pts, const float* centroids, size_t kc, const int32_t* assign,
                     int metric, double* out);

@@ -167,6 +167,9 @@ class Ref:
         lib.ref_random_sample.argtypes = [_f, _sz, _sz, _sz, C.c_int, _f]
         lib.ref_closest_leaders.argtypes = [_f, _sz, _sz, _f, _sz, C.c_uint32, C.c_int, _f, _u32, _u32]
         lib.ref_ivf_query.argtypes = [_f, _sz, _sz, _i32, _u32, _sz, _f, C.c_int, _i32, _sz, _f, _u32, _u32]
+        if hasattr(lib, "ref_balanced_kmeans"):
+            lib.ref_balanced_kmeans.restype = C.c_longlong
+            lib.ref_balanced_kmeans.argtypes = [_f, _sz, _sz, _f, _sz, _sz, _i32]
         if hasattr(lib, "ref_crunch_bucket"):
             lib.ref_crunch_bucket.argtypes = [_f, _sz, _sz, _u32, _sz, C.c_int, _f, _u32, _u32]
         lib.ref_pointset_create.restype = C.c_void_p
@@ -243,6 +246,13 @@ class Ref:
         self.lib.ref_closest_leaders(points, points.shape[0], points.shape[1], leaders, leaders.shape[0], my_id, k, dist,
                                      ids, cnt)
         return dist[:cnt[0]], ids[:cnt[0]]
+
+    def balanced_kmeans(self, points, centroids, max_cluster_size):
+        points = _f32(points)
+        cent = _f32(centroids).copy()
+        assign = np.empty(points.shape[0], np.int32)
+        kc = self.lib.ref_balanced_kmeans(points, points.shape[0], points.shape[1], cent, cent.shape[0], int(max_cluster_size), assign)
+        return assign, cent[:kc].copy()
 
     def crunch_bucket(self, points, bucket, k):
         points = _f32(points)

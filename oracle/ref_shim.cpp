@@ -158,6 +158,15 @@ void ref_ivf_query(const float* points, size_t n, size_t d, const int32_t* clust
     }
 }
 
+// BalancedKMeans (kmeans.cpp:251-524); prints its progress to stdout like the reference does.
+long long ref_balanced_kmeans(const float* points, size_t n, size_t d, float* centroids, size_t kc, size_t max_cluster_size, int32_t* out_assign) {
+    PointSet P = make_pointset(points, n, d), C = make_pointset(centroids, kc, d);
+    std::vector<int> a = BalancedKMeans(P, C, max_cluster_size);
+    for (size_t i = 0; i < n; ++i) out_assign[i] = a[i];
+    std::memcpy(centroids, C.coordinates.data(), C.n * d * sizeof(float));
+    return (long long) C.n;
+}
+
 // ApproximateKNNGraphBuilder::CrunchBucket (knn_graph.h:165-185): all pairs inside one bucket, per-member top-k of
 // (distance, global id); member j's list goes to out_*[j*k ..].
 void ref_crunch_bucket(const float* points, size_t n, size_t d, const uint32_t* bucket, size_t m, int k, float* out_dist,

@@ -91,6 +91,20 @@ def main():
     obj = ref_mips.objective(P, cent, assign)
     save("kmeans_mips_d48_k16", points=P, init=C0, assign=assign, centroids=cent, objective=np.float64(obj))
 
+    # BalancedKMeans (kmeans.cpp:251-524) on a skewed mixture: the reference's moving phase is racy, so the fixture records what
+    # parity means here -- every cluster within the bound, and the objective the reference reached
+    rng = np.random.default_rng(99)
+    sizes = [2600, 900, 300, 120, 60, 20]
+    centres = rng.standard_normal((len(sizes), 16)).astype(np.float32) * 5
+    P = np.concatenate([centres[c] + rng.standard_normal((m, 16)).astype(np.float32) for c, m in enumerate(sizes)]).astype(np.float32)
+    P = P[rng.permutation(len(P))]
+    C0 = ref.random_sample(P, 8, 555)
+    bound = 600
+    assign, cent = ref.balanced_kmeans(P, C0, bound)
+    obj = ref.objective(P, cent, assign)
+    save("balanced_kmeans", points=P, init=C0, max_cluster_size=np.int64(bound), assign=assign, centroids=cent, objective=np.float64(obj),
+         sizes=np.bincount(assign, minlength=len(cent)))
+
 
 if __name__ == "__main__":
     main()

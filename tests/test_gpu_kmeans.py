@@ -188,3 +188,25 @@ def test_kmeans_mips_build_golden(ctx, gpann_mod, oracle):
     for c in np.nonzero(s1)[0][:5]:
         want = (P[a1 == c] ** 2).sum(1).mean()
         assert abs((c1[c].astype(np.float64) ** 2).sum() - want) <= 1e-4 * want
+
+
+def test_balanced_kmeans_against_the_reference(ctx, gpann_mod, oracle):
+    """BalancedKMeans (src/kmeans.cpp:251-524).  The reference's moving phase is a racy parallel_for, so parity is what the
+    fixture records: every cluster within the bound, and an objective as good as the one the reference reached (5 %)."""
+    g = golden("balanced_kmeans")
+    P, bound = g["points"], int(g["max_cluster_size"])
+    pts = ctx.upload(P, storage=gpann_mod.STORAGE_F32)
+    assign, cent, sizes = ctx.balanced_kmeans(pts, g["init"], bound)
+    assert ctx.last_algo == "balanced_kmeans"
+    assert len(assign) == len(P) and assign.min() >= 0 and assign.max() < len(cent)
+    assert (np.bincount(assign, minlength=len(cent)) == sizes).all()
+    assert sizes.max() <= bound, sizes
+    assert int(g["sizes"].max()) <= bound
+    obj = oracle.objective(P, cent, assign)
+    assert obj <= 1.05 * float(g["objective"]), (obj, float(g["objective"]))
+    # plain KMeans on the same input violates the bound (otherwise the test would not exercise the moving phase)
+    a0, c0, s0 = ctx.kmeans_run(pts, g["init"], rounds=20)
+    assert s0.max() > bound
+    # a bound nobody exceeds returns the KMeans result unchanged (src/kmeans.cpp:283-284)
+    a1, c1, s1 = ctx.balanced_kmeans(pts, g["init"], len(P))
+    assert np.array_equal(a1, a0) and np.array_equal(s1, s0)
