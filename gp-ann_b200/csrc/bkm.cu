@@ -359,7 +359,9 @@ int sd_balanced_kmeans(gpann_ctx* ctx, const gpann_points* pts, float* centroids
     double round_penalty = 0.0, best_objective = DBL_MAX;
     while (round++ <= kMaxRounds) {
         // perm = random_shuffle(iota(n), random(round)) (:400): a sort of hashed keys on the device
-        bkm_perm_keys_kernel<<<blocks_for(ctx, n), 256, 0, st>>>((uint32_t*) ctx->sort_a.p, (uint32_t*) ctx->sort_c.p, n, (uint32_t) round);
+        const char* e_seed = std::getenv("GPANN_BKM_SEED");  // tests / experiments: a different shuffle sequence
+        const uint32_t seed = (uint32_t) round + (e_seed ? (uint32_t) std::atoi(e_seed) * 1000u : 0u);
+        bkm_perm_keys_kernel<<<blocks_for(ctx, n), 256, 0, st>>>((uint32_t*) ctx->sort_a.p, (uint32_t*) ctx->sort_c.p, n, seed);
         size_t tb = ctx->sort_tmp.cap;
         if (sort_pairs_u32(ctx->sort_tmp.p, tb, (uint32_t*) ctx->sort_a.p, (uint32_t*) ctx->sort_b.p, (uint32_t*) ctx->sort_c.p,
                            (uint32_t*) ctx->sort_d.p, n, 32, st) != cudaSuccess)
@@ -385,6 +387,10 @@ int sd_balanced_kmeans(gpann_ctx* ctx, const gpann_points* pts, float* centroids
         CU_TRY(ctx, cudaMemcpyAsync(&next_penalty, scal.p, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaMemcpyAsync(&objective, d_obj, 8, cudaMemcpyDeviceToHost, st));
         GP_TRY(fetch_sizes());
+        static const bool verbose = std::getenv("GPANN_BKM_VERBOSE") != nullptr;
+        if (verbose)
+            std::fprintf(stderr, "[gpann bkm] round = %d penalty %g largest cluster %llu constraint %zu objective %g next penalty %g\n", round,
+                         round_penalty, (unsigned long long) *std::max_element(h_sizes.begin(), h_sizes.end()), max_cluster_size, objective, next_penalty);
         if (balanced()) {
             if (objective < best_objective) {
                 best_objective = objective;

@@ -291,6 +291,7 @@ int sd_group_min_dist(gpann_ctx* ctx, const gpann_points* pts, const int32_t* gr
     p.group = d_group.as<int32_t>();
     p.ngroups = ngroups;
     p.queries = d_q.as<float>();
+    p.out_ordered = d_out.as<uint32_t>();
     p.nq = (int) nq;
     p.metric = metric;
     const int elem = pts->storage == GPANN_STORAGE_F32 ? 4 : 1;
