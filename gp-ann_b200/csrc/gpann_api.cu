@@ -540,7 +540,11 @@ int topk_stream_host(gpann_ctx* ctx, const void* host_rows, int host_kind, int s
     const bool host_f32 = host_kind == kHostF32;
     const size_t esz = host_f32 ? 4 : 1;
     const size_t tile = tc::kTileN;
-    size_t C = chunk_rows ? chunk_rows : (((size_t) 512 << 20) / (d * esz));  // ~512 MB of host rows per chunk
+    // default chunk: ~1/8 of the set, between 64 MB and 512 MB of host rows -- large enough to amortise the per-chunk layout
+    // build, small enough that a 1.6 GB shard (100M x 128 bytes over 8 GPUs) still has ~8 chunks to overlap H2D with the scan
+    const size_t total_bytes = n * d * esz;
+    const size_t chunk_bytes = std::min<size_t>((size_t) 512 << 20, std::max<size_t>((size_t) 64 << 20, total_bytes / 8));
+    size_t C = chunk_rows ? chunk_rows : chunk_bytes / (d * esz);
     C = std::min(((C + tile - 1) / tile) * tile, ((std::max<size_t>(n, 1) + tile - 1) / tile) * tile);
     const size_t nchunks = std::max<size_t>(1, (n + C - 1) / C);
     const char* src = (const char*) host_rows;

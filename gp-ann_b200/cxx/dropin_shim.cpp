@@ -140,4 +140,17 @@ int dropin_write_ground_truth(const char* path, const float* dist, const uint32_
     WriteGroundTruth(path, gt);
     return 0;
 }
+
+long long dropin_balanced_kmeans(const float* points, size_t n, size_t d, float* centroids, size_t kc, size_t max_cluster_size, int32_t* out_assign) {
+    try {
+        PointSet P = make_pointset(points, n, d), C = make_pointset(centroids, kc, d);
+        std::vector<int> a = BalancedKMeans(P, C, max_cluster_size);
+        for (size_t i = 0; i < n; ++i) out_assign[i] = a[i];
+        std::memcpy(centroids, C.coordinates.data(), C.n * d * sizeof(float));
+        return (long long) C.n;
+    } catch (const std::exception& e) {
+        std::cerr << e.what() << std::endl;
+        return -1;
+    }
+}
 }

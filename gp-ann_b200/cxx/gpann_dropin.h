@@ -28,6 +28,9 @@ constexpr int kMetric = GPANN_METRIC_L2;
 
 struct Session {
     gpann_ctx* ctx = nullptr;
+    gpann_ctx* single = nullptr;  // entry points that take a single-device ctx (BalancedKMeans, segmented scans): ctx itself, or
+                                  // a ctx on the group's first device created on first use
+    int first_device = 0;
     std::mutex mutex;
     Session() {
         std::vector<int> devices;
@@ -41,13 +44,26 @@ struct Session {
             }
         }
         const char* dev = std::getenv("GPANN_DEVICE");
-        const int rc = devices.size() > 1 ? gpann_init_multi(&ctx, devices.data(), (int) devices.size())
-                                          : gpann_init(&ctx, !devices.empty() ? devices[0] : (dev ? std::atoi(dev) : 0));
+        first_device = !devices.empty() ? devices[0] : (dev ? std::atoi(dev) : 0);
+        const int rc = devices.size() > 1 ? gpann_init_multi(&ctx, devices.data(), (int) devices.size()) : gpann_init(&ctx, first_device);
         if (rc != 0)
             throw std::runtime_error("gpann: no usable CUDA device (gpann_init returned " + std::to_string(rc) +
                                      "); the GPU hot path has no CPU fallback");
     }
-    ~Session() { gpann_destroy(ctx); }
+    ~Session() {
+        if (single && single != ctx) gpann_destroy(single);
+        gpann_destroy(ctx);
+    }
+    gpann_ctx* single_device() {
+        if (!single) {
+            if (gpann_num_devices(ctx) == 1) single = ctx;
+            else if (gpann_init(&single, first_device) != 0) throw std::runtime_error("gpann: cannot create a single-device context");
+        }
+        return single;
+    }
+    void check_single(int rc) const {
+        if (rc != 0) throw std::runtime_error(std::string("gpann: ") + gpann_last_error(single));
+    }
     void check(int rc) const {
         if (rc != 0) throw std::runtime_error(std::string("gpann: ") + gpann_last_error(ctx));
     }

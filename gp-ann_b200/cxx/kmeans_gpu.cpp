@@ -1,4 +1,5 @@
-// kmeans_gpu.cpp -- KMeans / ObjectiveValue / RandomSample of the drop-in layer.
+// kmeans_gpu.cpp -- KMeans / BalancedKMeans / ObjectiveValue / RandomSample of the drop-in layer: everything gp-ann's
+// src/kmeans.h declares, so this file REPLACES src/kmeans.cpp in a gp-ann build.
 //   KMeans (reference src/kmeans.cpp:228-244): 20 fixed Lloyd rounds = ONE gpann_kmeans_run call (nearest centroid with
 //   first-minimum ties + deterministic per-cluster sums + division + empty-cluster removal, all on the GPU(s); on a group
 //   ctx the sums and counts are all-reduced over NCCL every round).  Points are uploaded once per call.
@@ -41,6 +42,27 @@ std::vector<int> KMeans(PointSet& P, PointSet& centroids) {
     size_t kept = centroids.n;
     s.check(gpann_kmeans_run(s.ctx, dp.h, centroids.coordinates.data(), centroids.n, NUM_ROUNDS, gpann_dropin::kMetric,
                              closest_center.data(), nullptr, &kept));
+    centroids.n = kept;
+    centroids.coordinates.resize(kept * centroids.d);
+    return closest_center;
+}
+
+// BalancedKMeans (src/kmeans.cpp:251-524): KMeans + the BKM+ penalty rounds, every distance on the GPU (gpann_balanced_kmeans).
+// The reference's progress prints are not reproduced.  `centroids` is updated in place and may shrink (the final
+// AggregateClustersParallel removes empty clusters, :477).
+std::vector<int> BalancedKMeans(PointSet& points, PointSet& centroids, size_t max_cluster_size) {
+    if (centroids.n < 1) throw std::runtime_error("KMeans #centroids < 1");
+    auto& s = gpann_dropin::session();
+    std::lock_guard<std::mutex> lock(s.mutex);
+    gpann_ctx* one = s.single_device();
+    gpann_points* h = nullptr;
+    s.check_single(gpann_points_upload(one, points.coordinates.data(), points.n, points.d, GPANN_STORAGE_F32, 0, &h));
+    std::vector<int> closest_center(points.n, -1);
+    size_t kept = centroids.n;
+    const int rc = gpann_balanced_kmeans(one, h, centroids.coordinates.data(), centroids.n, max_cluster_size, gpann_dropin::kMetric,
+                                         closest_center.data(), nullptr, &kept);
+    gpann_points_free(h);
+    s.check_single(rc);
     centroids.n = kept;
     centroids.coordinates.resize(kept * centroids.d);
     return closest_center;

@@ -1,6 +1,5 @@
-// kmeans.h -- drop-in for gp-ann's src/kmeans.h:5-8 (same signatures).  RandomSample, KMeans and ObjectiveValue are
-// implemented in kmeans_gpu.cpp over libgpann_cuda; BalancedKMeans (kmeans.cpp:253-524, SURVEY.md 8f "next") is
-// declared for source compatibility and is still provided by the reference's own kmeans.cpp.
+// kmeans.h (standalone builds only) -- gp-ann's src/kmeans.h:5-8, same signatures; all four are implemented in
+// ../kmeans_gpu.cpp over libgpann_cuda.
 #pragma once
 
 #include <cstddef>
