@@ -135,6 +135,21 @@ def bind_to_gpu_numa(gpu_index):
             return {"numa_node": node, "cpus": len(cpus)}
     except Exception:
         pass
+    try:  # fall-back: the "CPU Affinity" column of `nvidia-smi topo -m`
+        for line in subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout.splitlines():
+            f = line.split()
+            if f and f[0] == f"GPU{gpu_index}":
+                aff = next(x for x in f[1:] if x[0].isdigit() and ("-" in x or "," in x))
+                cpus = set()
+                for part in aff.split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return {"cpu_affinity": aff, "cpus": len(cpus)}
+    except Exception:
+        pass
     return None
 
 

@@ -173,14 +173,16 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     p.cap = pow2_ceil(k + kStreamTile);
     p.vec_ok = (((uintptr_t) pts->rows + row_begin * pts->pitch) % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
     const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
-    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16;
+    // per query: float row, candidate buffer, threshold + count; byte storage adds the query packed as bytes (qpitch bytes,
+    // a multiple of 16) + its integer norm + the "integer-valued" flag of the dp4a path
+    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16 + (elem == 1 ? (size_t) ((p.qpitch + 15) & ~15) + 16 : 0);
     const size_t budget = 160 * 1024;
     if (tile_bytes + per_q > 200 * 1024)
         return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile (f32: d <= 384)");
     const int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16),
                                           std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
     p.qb = qb;
-    const size_t smem = tile_bytes + (size_t) qb * per_q;
+    const size_t smem = tile_bytes + (size_t) qb * per_q + 16;  // + alignment slack of the packed byte queries
     const size_t nrows = row_end - row_begin;
     const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));

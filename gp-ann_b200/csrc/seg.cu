@@ -26,7 +26,7 @@ __device__ __forceinline__ float elem_as_float(const char* row, int storage, int
 }
 
 template <int STORAGE>
-__global__ void __launch_bounds__(kStreamTile) seg_scan_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kStreamTile, 5) seg_scan_kernel(const SegParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int elem = STORAGE == kF32 ? 4 : 1;
