@@ -882,6 +882,7 @@ int kmeans_assign_tensor(gpann_ctx* ctx, const gpann_points* pts, const float* d
     a.partial = (uint4*) ctx->km_partial.p;
     a.idesc = kmtc::make_idesc_bf16(NB);
     a.mode = ctx->km_mode;
+    a.pack_mask = 0xFFFFFFE0u;
     const unsigned groups = (unsigned) std::max<size_t>(1, std::min<size_t>((size_t) (ctx->num_sms / CS), a.ntiles));
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
     launch_kmeans_tc(pts->km_tmap, tmap_b, a, groups * CS, kmtc::smem_bytes(NB, nkb, stages), st);

@@ -279,6 +279,7 @@ struct Args {
     uint4* partial;          // [CS][ntiles*128] per point: top-3 packed scores + chunk ids
     uint32_t idesc;
     int mode;                // 0 = full; 2 = probe: MMA issue only (results invalid)
+    uint32_t pack_mask;      // 0xFFFFFFE0, passed as an argument so that (score & mask) | column stays one LOP3 (kmeans_tc.cu)
 };
 
 inline size_t smem_bytes(int NB, int nkb, int stages) {

@@ -249,19 +249,19 @@ __device__ __forceinline__ float exact_sqr_l2(const float* __restrict__ x, const
 
 // Insert one record.  k <= 32: unsorted list of the k best with replace-the-maximum (exact threshold after every
 // insert).  Larger k: append; the caller compacts a full list warp-wide.  Returns true if the list needs compaction.
-template <bool kFloat>
+template <bool kFloat, bool kMips>
 __device__ __forceinline__ void apply_bound(const SelState& s, uint32_t qs, float kth_dist) {
     if (kFloat) {  // U = |q|^2 - kth (MIPS: 1 - kth), float bits in the int arrays; monotone non-decreasing
-        const float u = (s.mips ? 1.f : __int_as_float(s.nq[qs])) - kth_dist;
+        const float u = (kMips ? 1.f : __int_as_float(s.nq[qs])) - kth_dist;
         s.U[qs] = __float_as_int(fmaxf(__int_as_float(s.U[qs]), u));
     } else {
-        s.U[qs] = max(s.U[qs], (s.mips ? 1 : s.nq[qs]) - (int) kth_dist);
+        s.U[qs] = max(s.U[qs], (kMips ? 1 : s.nq[qs]) - (int) kth_dist);
     }
 }
-template <bool kFloat>
+template <bool kFloat, bool kMips>
 __device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs, uint64_t kth) {
     const float kd = key_dist(kth);
-    apply_bound<kFloat>(s, qs, kd);
+    apply_bound<kFloat, kMips>(s, qs, kd);
     // distances are non-negative, so their bit patterns order like unsigned integers
     if (s.gbound && kd >= 0.f) {
         const uint32_t bits = __float_as_uint(kd);
@@ -269,14 +269,14 @@ __device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs
     }
 }
 // Pull the bounds other point splits have published for this selection warp's queries into the filter thresholds.
-template <bool kFloat>
+template <bool kFloat, bool kMips>
 __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int lane) {
     if (!s.gbound) return;
     for (int base = sel * 32; base < s.nslots; base += 32 * kSelWarps) {
         const uint32_t qs = (uint32_t) (base + lane);
         const uint32_t bits = __ldcg(s.gbound + qs);
         const float b = __uint_as_float(bits);
-        if (b < 3.0e38f) apply_bound<kFloat>(s, qs, b);
+        if (b < 3.0e38f) apply_bound<kFloat, kMips>(s, qs, b);
         if (s.npeers > 0) {  // this selection warp owns the bitmap words of its slots: plain read-and-clear by lane 0
             uint32_t word = 0;
             if (lane == 0) word = atomicExch(s.dirty + (base >> 5), 0u);
@@ -287,14 +287,14 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
     }
 }
 
-template <bool kFloat>
+template <bool kFloat, bool kMips>
 __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key, uint32_t extra) {
     if (kFloat) {  // the record holds (accumulator, id) and the point's norm
         const uint32_t id = (uint32_t) key;
         const uint64_t kth_now = s.kth[qs];
         if (kth_now != kEmptyKey) {  // same test as the filter's, with this point's own norm and the current k-th distance
             const float nqv = __int_as_float(s.nq[qs]), nx = __uint_as_float(extra), acc = __uint_as_float((uint32_t) (key >> 32));
-            const float lb = s.mips ? 1.f - acc - (s.eps * sqrtf(nqv * nx) + 1e-5f * (1.f + fabsf(acc)))
+            const float lb = kMips ? 1.f - acc - (s.eps * sqrtf(nqv * nx) + 1e-5f * (1.f + fabsf(acc)))
                                     : nqv + nx - 2.f * acc - (2.f * s.eps * sqrtf(nqv * nx) + 1e-5f * (nqv + nx));
             if (lb - 1e-6f * fabsf(lb) > key_dist(kth_now)) return false;
         }
@@ -302,7 +302,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         // the row is a random 4*d bytes of HBM: request all of its lines at once instead of one miss per loop trip
         for (int off = 128; off < s.d * 4; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xrow) + off));
         float dist;
-        if (s.mips) {  // inner_product (src/dist.cpp:42-48): sequential FMA; mips_distance = 1 - <p,q>
+        if (kMips) {  // inner_product (src/dist.cpp:42-48): sequential FMA; mips_distance = 1 - <p,q>
             const float* qrow = s.q_f32 + (size_t) qs * s.d;
             float r = 0.f;
             for (int i = 0; i < s.d; ++i) r = __fmaf_rn(qrow[i], xrow[i], r);
@@ -340,7 +340,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         }
         s.kth[qs] = m;
         s.maxpos[qs] = mp;
-        publish_threshold<kFloat>(s, qs, m);
+        publish_threshold<kFloat, kMips>(s, qs, m);
         return false;
     }
     if (key >= s.kth[qs]) return false;
@@ -349,7 +349,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     return cnt >= s.cap;
 }
 
-template <bool kFloat>
+template <bool kFloat, bool kMips>
 __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel,
                                                  unsigned long long* stats) {
     uint32_t head = 0, idle = 0, busy = 0;
@@ -362,7 +362,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         const uint32_t avail = tail - head;
         if (avail == 0) {
             if (finished == (uint32_t) kEpiWarps) break;
-            if ((++idle & 7u) == 0) refresh_bounds<kFloat>(s, sel, lane);  // every ~8 us of idling
+            if ((++idle & 7u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);  // every ~8 us of idling
             busy = 0;
             __nanosleep(GPANN_SEL_SLEEP);  // an idle selection warp should cost (almost) no issue slots or power
             ++n_idle;
@@ -400,7 +400,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             bool compact = false;
             if (pending && (__ffs(peers) - 1) == lane) {
-                compact = select_insert<kFloat>(s, qs, key, extra);
+                compact = select_insert<kFloat, kMips>(s, qs, key, extra);
                 pending = false;
             }
             __syncwarp();
@@ -414,14 +414,14 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                 if (lane == L) {
                     s.cnt[qsL] = s.k;
                     s.kth[qsL] = newkth;
-                    publish_threshold<kFloat>(s, qsL, newkth);
+                    publish_threshold<kFloat, kMips>(s, qsL, newkth);
                 }
                 __syncwarp();
             }
         }
         if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
         // a busy selection warp (cold start) still trades bounds with the other splits / ranks now and then
-        if (s.npeers > 0 && (++busy & 15u) == 0) refresh_bounds<kFloat>(s, sel, lane);
+        if (s.npeers > 0 && (++busy & 15u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);
     }
     if (stats && lane == 0 && sel == 0 && blockIdx.x == 0) {  // diagnostics (GPANN_TC_STATS)
         stats[16] = n_batches;
@@ -950,7 +950,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         for (int pi = 0; pi < kMaxPeers; ++pi) ss.peer[pi] = pi < a.npeers ? a.peer_bound[pi] + qbase : nullptr;
         ss.dirty = s_dirty;
         ss.nslots = nslots;
-        selection_warp_loop<kFloat>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
+        if (a.mips) selection_warp_loop<kFloat, true>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
+        else selection_warp_loop<kFloat, false>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
     }
 
