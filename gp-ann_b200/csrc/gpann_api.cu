@@ -315,7 +315,16 @@ struct TcLaunch {
     size_t smem = 0, part_keys = 0;
     uint32_t tiles_total = 0;
     uint64_t* carry_keys = nullptr;  // ctx->partial part 0
+    size_t flog_tail_bytes = 0, flog_bytes = 0;  // find log (tc::Args::flog): cleared before every launch
 };
+
+// The find log starts every launch empty: tails 0, entries 0xFF (= not written).
+int tc_flog_reset(gpann_ctx* ctx, const TcLaunch& L, cudaStream_t st) {
+    if (!L.a.flog) return 0;
+    CU_TRY(ctx, cudaMemsetAsync(L.a.flog_tail, 0, L.flog_tail_bytes, st));
+    CU_TRY(ctx, cudaMemsetAsync(L.a.flog, 0xFF, L.flog_bytes, st));
+    return 0;
+}
 
 int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L) {
     const int k = pl.k;
@@ -359,6 +368,16 @@ int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L)
     a.mips = pl.mips;
     L.grid = (unsigned) (pl.G * L.S);
     L.smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
+    // find log: several point splits serve each query group and the lists sit in shared memory (k <= 16)
+    static const bool no_flog = std::getenv("GPANN_TC_NOLOG") != nullptr;
+    if (!no_flog && pl.lists_smem && L.S > 1 && ctx->tc_mode == 0) {
+        a.flog_cap = (uint32_t) (pl.R * tc::kTileM) * 64u;  // ~k (1 + ln(n / sample)) finds per query are expected; overflow only loses sharing
+        L.flog_tail_bytes = ((size_t) pl.G * sizeof(uint32_t) + 255) & ~(size_t) 255;
+        L.flog_bytes = (size_t) pl.G * a.flog_cap * sizeof(uint4);
+        GP_TRY(reserve(ctx, ctx->flog, L.flog_tail_bytes + L.flog_bytes));
+        a.flog_tail = (uint32_t*) ctx->flog.p;
+        a.flog = (uint4*) ((char*) ctx->flog.p + L.flog_tail_bytes);
+    }
     return 0;
 }
 
@@ -388,12 +407,16 @@ int tc_sample(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, cudaStream_
         a.tile_stride = L.tiles_total / nsample;
         a.tile_lo = a.tile_stride / 2;
         a.sample_pass = 1;
+        // no find log in the sample passes: they are bound by the selection warps (a cold pass accepts nearly every record),
+        // and sharing would multiply exactly that work by the number of splits (measured: 2.0M -> 5.9M clk for the three levels)
+        a.flog = nullptr;
         static const char* e_sst = std::getenv("GPANN_TC_STATS");
         if (e_sst && std::atoi(e_sst) >= 2) {
             GP_TRY(reserve(ctx, ctx->misc, 256));
             CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
             a.stats = (unsigned long long*) ctx->misc.p;
         }
+        GP_TRY(tc_flog_reset(ctx, L, st));
         launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, L.grid, L.smem, st);
         GP_TRY(check_launch(ctx, "topk_tc_kernel(sample)"));
         if (a.stats) {
@@ -442,6 +465,7 @@ int tc_main(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool carry, b
         CU_TRY(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, st));
         a.stats = (unsigned long long*) ctx->misc.p;
     }
+    GP_TRY(tc_flog_reset(ctx, L, st));
     if (ctx->timing) cudaEventRecord(ctx->ev0, st);
     launch_topk_tc(pl.is_float, *lay.tmap, pl.tmap_q, a, L.grid, L.smem, st);
     if (ctx->timing) {
@@ -1087,7 +1111,7 @@ void sd_destroy(gpann_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();  // asynchronous entry points may still be running on caller streams
     comm_destroy(ctx);
-    DevBuf* bufs[] = { &ctx->pace, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
+    DevBuf* bufs[] = { &ctx->pace, &ctx->flog, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
                        &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info,

@@ -48,6 +48,10 @@
 #endif
 // (A software-pipelined drain -- the next chunk pair's TMEM loads queued behind the current pair's max trees, across items --
 // was built and measured in round 2: 150 vs 96 ms at 100M, see profiles/r2_summary.md; commit 84d16f3 has the code.)
+// 1: the lean drain (all 128 columns of a filter warp in registers, one max tree + one branch per item, out-of-line hit scan)
+#ifndef GPANN_LEAN
+#define GPANN_LEAN 0
+#endif
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
 #endif
@@ -176,6 +180,29 @@ __device__ __forceinline__ void enqueue_chunk_f(const uint32_t (&v)[32], float T
     }
 }
 
+// ---- lean drain (GPANN_LEAN, the production filter loop) -----------------------------------------------------------------
+// A filter warp pulls ALL of its 128 columns of an item into registers with four x32 loads, hands the accumulator slot back
+// and only then reduces: four 32-value max trees, ONE compare and ONE branch per item.  A lane that holds a value at or above
+// its threshold passes the 32-column chunk(s) in question through local memory to the out-of-line copy of enqueue_chunk
+// below (eight 16-byte stores and loads; the select trees then run on registers again), so the hot loop carries neither the
+// hit-mask builders nor the select trees.  The hit path must stay SHORT: with two accumulator slots a warp that lingers
+// stalls the MMA issuer after one more item (a serial scan of the lane's values from local memory cost 2x on the whole pass).
+template <bool kFloat>
+__device__ __noinline__ void slow_chunk(const uint32_t* vp, uint32_t Tbits, const int32_t* tn, const uint32_t* ti, int col0, int nqv,
+                                        uint32_t qs, uint32_t* q_tail, volatile uint32_t* q_head, uint4* q_rec, uint32_t q_cap,
+                                        int mips) {
+    Queue q;
+    q.cap = q_cap;
+    q.rec = q_rec;
+    q.tail = q_tail;
+    q.head = q_head;
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = vp[j];
+    if (kFloat) enqueue_chunk_f(v, __uint_as_float(Tbits), tn, ti, col0, qs, q);
+    else enqueue_chunk(v, (int) Tbits, tn, ti, col0, nqv, qs, q, mips);
+}
+
 // Per-query selection state owned by the selection warps (shared memory, indexed by query slot qs).
 struct SelState {
     uint64_t* kth;   // current k-th best key (kEmptyKey until k keys are held)
@@ -203,7 +230,22 @@ struct SelState {
     int d;
     uint32_t id_base;
     float eps;
+    // find log of this CTA's query group (Args::flog): every accepted key of this CTA is appended, the other splits'
+    // entries are applied to the lists as FOREIGN keys (they tighten the k-th distance but are not part of this CTA's output:
+    // own[qs] marks the list positions that hold this CTA's own finds)
+    uint4* flog;
+    uint32_t* flog_tail;
+    uint32_t flog_cap, split;
+    uint16_t* own;
 };
+
+__device__ __forceinline__ void log_find(const SelState& s, uint32_t qs, uint64_t key) {
+    const uint32_t pos = atomicAdd(s.flog_tail, 1u);
+    if (pos < s.flog_cap) {
+        uint4 e = make_uint4((uint32_t) key, (uint32_t) (key >> 32), qs | (s.split << 16), 0u);
+        asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(s.flog + pos), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+    }
+}
 
 // Squared L2 distance of two fp32 rows in the reference's summation order (src/dist.cpp:9-16 ->
 // hnswlib space_l2.h:60-91, 6-20): 8 interleaved FMA lanes over the leading multiple of 16, lanes added in order, then
@@ -288,8 +330,8 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
 }
 
 template <bool kFloat, bool kMips>
-__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key, uint32_t extra) {
-    if (kFloat) {  // the record holds (accumulator, id) and the point's norm
+__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key, uint32_t extra, bool foreign = false) {
+    if (kFloat && !foreign) {  // the record holds (accumulator, id) and the point's norm
         const uint32_t id = (uint32_t) key;
         const uint64_t kth_now = s.kth[qs];
         if (kth_now != kEmptyKey) {  // same test as the filter's, with this point's own norm and the current k-th distance
@@ -316,13 +358,20 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     int cnt = s.cnt[qs];
     if (s.k <= 32) {
         if (cnt < s.k) {
+            if (s.flog) s.own[qs] = (uint16_t) ((s.own[qs] & ~(1u << cnt)) | (foreign ? 0u : 1u << cnt));
             list[cnt++] = key;
             s.cnt[qs] = cnt;
-            if (cnt < s.k) return false;
+            if (cnt < s.k) {
+                if (s.flog && !foreign) log_find(s, qs, key);
+                return false;
+            }
         } else {
             if (key >= s.kth[qs]) return false;
-            list[s.maxpos[qs]] = key;
+            const int mp0 = s.maxpos[qs];
+            list[mp0] = key;
+            if (s.flog) s.own[qs] = (uint16_t) ((s.own[qs] & ~(1u << mp0)) | (foreign ? 0u : 1u << mp0));
         }
+        if (s.flog && !foreign) log_find(s, qs, key);
         // new maximum of the list: the keys sit in global memory (L2), so the loads are issued eight at a time instead
         // of one dependent load per key (a record cost ~3 us of selection-warp time before, ~1M records per sample pass)
         uint64_t m = 0;
@@ -349,10 +398,39 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     return cnt >= s.cap;
 }
 
+// Apply the other splits' new finds (the group's find log) to this selection warp's lists.  Never blocks: an entry that is
+// reserved but not yet written ends the round, the next poll resumes there.
+template <bool kFloat, bool kMips>
+__device__ __forceinline__ void poll_log(const SelState& s, uint32_t& log_read, int sel, int lane) {
+    if (!s.flog) return;
+    const uint32_t tail = min(__ldcg(s.flog_tail), s.flog_cap);
+    while (log_read < tail) {
+        const uint32_t n = min(tail - log_read, 32u);
+        uint4 e = make_uint4(0u, 0u, kQEmpty, 0u);
+        if ((uint32_t) lane < n)
+            asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(s.flog + log_read + lane) : "memory");
+        const unsigned notready = __ballot_sync(0xffffffffu, (uint32_t) lane < n && e.z == kQEmpty);
+        const uint32_t m = notready ? (uint32_t) (__ffs(notready) - 1) : n;
+        const uint32_t qs = e.z & 0xFFFFu;
+        bool pending = (uint32_t) lane < m && (e.z >> 16) != s.split && ((qs >> 5) & (uint32_t) (kSelWarps - 1)) == (uint32_t) sel;
+        const uint64_t key = ((uint64_t) e.y << 32) | e.x;
+        while (__any_sync(0xffffffffu, pending)) {  // entries for the same query: one per round, lowest lane first
+            const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
+            if (pending && (__ffs(peers) - 1) == lane) {
+                select_insert<kFloat, kMips>(s, qs, key, 0u, true);
+                pending = false;
+            }
+            __syncwarp();
+        }
+        log_read += m;
+        if (m < n) break;
+    }
+}
+
 template <bool kFloat, bool kMips>
 __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s, volatile uint32_t* done, int lane, int sel,
                                                  unsigned long long* stats) {
-    uint32_t head = 0, idle = 0, busy = 0;
+    uint32_t head = 0, idle = 0, busy = 0, log_read = 0;
     unsigned long long n_batches = 0, n_rounds = 0, n_idle = 0, clk_insert = 0, clk_pop = 0;
     while (true) {
         const long long c_top = stats ? clock64() : 0;
@@ -363,6 +441,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         if (avail == 0) {
             if (finished == (uint32_t) kEpiWarps) break;
             if ((++idle & 7u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);  // every ~8 us of idling
+            poll_log<kFloat, kMips>(s, log_read, sel, lane);
             busy = 0;
             __nanosleep(GPANN_SEL_SLEEP);  // an idle selection warp should cost (almost) no issue slots or power
             ++n_idle;
@@ -421,7 +500,9 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         }
         if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
         // a busy selection warp (cold start) still trades bounds with the other splits / ranks now and then
-        if (s.npeers > 0 && (++busy & 15u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);
+        ++busy;
+        if (s.npeers > 0 && (busy & 15u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);
+        if ((busy & 3u) == 0) poll_log<kFloat, kMips>(s, log_read, sel, lane);
     }
     if (stats && lane == 0 && sel == 0 && blockIdx.x == 0) {  // diagnostics (GPANN_TC_STATS)
         stats[16] = n_batches;
@@ -489,6 +570,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int* s_maxpos = s_nq + R * kTileM;
     uint64_t* s_lists = reinterpret_cast<uint64_t*>(s_maxpos + R * kTileM);   // [R*128][kSmemListKeys] when a.lists_smem
     uint32_t* s_dirty = reinterpret_cast<uint32_t*>(s_lists + (a.lists_smem ? (size_t) R * kTileM * kSmemListKeys : 0));  // [R*4]
+    uint16_t* s_own = reinterpret_cast<uint16_t*>(s_dirty + 16);  // [R*128] when a.lists_smem: list positions holding own finds
+    const bool use_flog = a.flog != nullptr && a.lists_smem;
 
     const int nslots = R * kTileM;
     const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
@@ -496,6 +579,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         s_kth[i] = kEmptyKey;
         s_cnt[i] = 0;
         s_maxpos[i] = 0;
+        if (use_flog) s_own[i] = 0;
         // warm start: an upper bound on this query's kth distance from the sample passes (+inf = none)
         const float b = a.bound ? __uint_as_float(a.bound[qbase + i]) : __int_as_float(0x7f800000);
         // Padding slots (query index >= nq) hold zero vectors: left alone, every low-norm point "beats" their k-th
@@ -775,7 +859,112 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         const int sample_pass = a.sample_pass;
         const float eps = a.eps;
         const int mips = a.mips;
-        for (uint32_t t = tile_begin; t < tile_end; ++t) {
+        // ===== lean drain: the production loop (see slow_chunk above) =====
+        constexpr bool kLean = GPANN_LEAN && !kProbe && !kFilterByItem && kHalves == 1 && kColsPerWarp == 128 && kSlots == 2;
+        for (uint32_t t = tile_begin; kLean && t < tile_end; ++t) {
+            mbar_wait(bar_full + 8 * st, ph);
+            const int32_t* tn = s_norm + st * kTileN;
+            const uint32_t* ti = s_id + st * kTileN;
+            const int nmin1 = tn[0] + 1;
+            const float nmin_f = __int_as_float(tn[0]), nmax_f = __int_as_float(tn[kAccN - 1]);
+            const float rmin_f = kFloat ? sqrtf(nmin_f) : 0.f, rmax_f = kFloat ? sqrtf(nmax_f) : 0.f;
+            for (int r = 0; r < R; ++r) {
+                const uint32_t qs = (uint32_t) (r * kTileM + qrow);
+                const int Uraw = *reinterpret_cast<volatile int*>(s_U + qs);
+                const int nqraw = s_nq[qs];
+                int Ti = 0;
+                float Tf = 0.f;
+                if (kFloat) {  // derivation: the generic loop below
+                    const float nqv = __int_as_float(nqraw), U = __int_as_float(Uraw);
+                    const float sq = 2.f * eps * sqrtf(nqv);
+                    const float g0 = nmin_f - sq * rmin_f - 1e-5f * (nqv + nmin_f);
+                    const float g1 = nmax_f - sq * rmax_f - 1e-5f * (nqv + nmax_f);
+                    float gmin = fminf(g0, g1);
+                    const float nstar = eps * eps * nqv;
+                    if (nmin_f <= 1.001f * nstar && nstar <= 1.001f * nmax_f) gmin = -1.001f * nstar - 2e-5f * nqv;
+                    Tf = 0.5f * (U + gmin);
+                    if (mips) {
+                        const float qx = sqrtf(nqv) * rmax_f;
+                        Tf = U - eps * qx - 1e-5f * (1.f + fabsf(U) + qx);
+                    }
+                    Tf -= 1e-6f * fabsf(Tf);
+                } else {
+                    Ti = mips ? Uraw : (Uraw + nmin1) >> 1;
+                }
+                mbar_wait(bar_tfull + 8 * slot, sph);
+                tcgen05_fence_after();
+                const uint32_t tbase = tbase0 + slot * kAccN;
+                // kLeanGroups loads of (4 / kLeanGroups) x 32 columns: 1 = everything up front (128 data registers), 2 = two
+                // 64-column phases like the generic loop (the slot goes back after the second load)
+                constexpr int kLeanGroups = GPANN_LEAN == 2 ? 2 : 1, kPer = 4 / kLeanGroups;
+                const uint32_t slot_now = slot;
+                if (++slot == (uint32_t) kSlots) {
+                    slot = 0;
+                    sph ^= 1;
+                }
+#pragma unroll
+                for (int gq = 0; gq < kLeanGroups; ++gq) {
+                    uint32_t v[kPer][32];
+#pragma unroll
+                    for (int c = 0; c < kPer; ++c) tmem_ld32(tbase + (gq * kPer + c) * 32, v[c]);
+                    tmem_wait_ld();            // warp-wide (.sync.aligned): every lane's columns are in registers
+                    if (gq == kLeanGroups - 1) {
+                        tcgen05_fence_before();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot_now);  // slot back to the MMA issuer before the arithmetic
+                    }
+                    // chunk maxima, one compare, one (divergent) branch
+                    if (kFloat) {
+                        float m[kPer], mm;
+#pragma unroll
+                        for (int c = 0; c < kPer; ++c) m[c] = max32f(v[c]);
+                        mm = m[0];
+#pragma unroll
+                        for (int c = 1; c < kPer; ++c) mm = fmaxf(mm, m[c]);
+                        if (mm >= Tf) {
+                            const bool cold = sample_pass && Tf < -1.0e37f;
+#pragma unroll
+                            for (int c = 0; c < kPer; ++c) {
+                                if (m[c] >= Tf) {
+                                    uint32_t tmp[32];
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) tmp[j] = v[c][j];
+                                    slow_chunk<true>(tmp, __float_as_uint(cold ? m[c] : Tf), tn, ti, col_base + 32 * (gq * kPer + c), nqraw, qs,
+                                                     q.tail, q.head, q.rec, q.cap, mips);
+                                }
+                            }
+                        }
+                    } else {
+                        int m[kPer], mm;
+#pragma unroll
+                        for (int c = 0; c < kPer; ++c) m[c] = max32(v[c]);
+                        mm = m[0];
+#pragma unroll
+                        for (int c = 1; c < kPer; ++c) mm = max(mm, m[c]);
+                        if (mm >= Ti) {
+                            const bool cold = sample_pass && Ti < -(1 << 28);
+#pragma unroll
+                            for (int c = 0; c < kPer; ++c) {
+                                if (m[c] >= Ti) {
+                                    uint32_t tmp[32];
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) tmp[j] = v[c][j];
+                                    slow_chunk<false>(tmp, (uint32_t) (cold ? m[c] : Ti), tn, ti, col_base + 32 * (gq * kPer + c), nqraw, qs,
+                                                      q.tail, q.head, q.rec, q.cap, mips);
+                                }
+                            }
+                        }
+                    }
+                    if (gq + 1 < kLeanGroups) __syncwarp();
+                }
+                __syncwarp();  // the next tcgen05.ld is .aligned
+            }
+            if (lane == 0) mbar_arrive(bar_empty + 8 * st);  // this warp no longer needs the tile's norms/ids
+            if (++st == (uint32_t) NST) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        for (uint32_t t = tile_begin; !kLean && t < tile_end; ++t) {
             // the tile's norms/ids arrive with its operands; the MMA is ahead of us, so this is normally immediate
             const long long c0 = stats ? clock64() : 0;
             mbar_wait(bar_full + 8 * st, ph);
@@ -950,6 +1139,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         for (int pi = 0; pi < kMaxPeers; ++pi) ss.peer[pi] = pi < a.npeers ? a.peer_bound[pi] + qbase : nullptr;
         ss.dirty = s_dirty;
         ss.nslots = nslots;
+        ss.flog = use_flog ? a.flog + (size_t) g * a.flog_cap : nullptr;
+        ss.flog_tail = use_flog ? a.flog_tail + g : nullptr;
+        ss.flog_cap = a.flog_cap;
+        ss.split = (uint32_t) s;
+        ss.own = s_own;
         if (a.mips) selection_warp_loop<kFloat, true>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         else selection_warp_loop<kFloat, false>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
@@ -963,6 +1157,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             const uint64_t* b = my_lists + (size_t) qs * lstride;
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
             const int cnt = s_cnt[qs];
+            if (use_flog) {  // the other splits' keys served the threshold only: they are not this CTA's to report
+                if (lane < cnt && !((s_own[qs] >> lane) & 1u)) my_lists[(size_t) qs * lstride + lane] = kEmptyKey;
+                __syncwarp();
+            }
             warp_select_topk_dyn<16>(b, cnt, a.k, dst, lane, min(a.cap, max(32, pow2_ceil(max(cnt, a.k)))));
         }
     }
