@@ -368,10 +368,12 @@ int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L)
     a.mips = pl.mips;
     L.grid = (unsigned) (pl.G * L.S);
     L.smem = tc::smem_bytes(pl.R, pl.kblocks, pl.stages, pl.qcap, pl.lists_smem);
-    // find log: several point splits serve each query group and the lists sit in shared memory (k <= 16)
-    static const bool no_flog = std::getenv("GPANN_TC_NOLOG") != nullptr;
+    // find log: several point splits serve each query group.  Small k only (lists in shared memory): at k = 100 every CTA
+    // re-applying the whole group's finds to lists in L2 costs more than the tighter thresholds save (C2: 65 -> 78 ms).
+    const bool no_flog = std::getenv("GPANN_TC_NOLOG") != nullptr;  // (not cached: the parity test toggles it)
     if (!no_flog && pl.lists_smem && L.S > 1 && ctx->tc_mode == 0) {
-        a.flog_cap = (uint32_t) (pl.R * tc::kTileM) * 64u;  // ~k (1 + ln(n / sample)) finds per query are expected; overflow only loses sharing
+        // ~k (1 + ln(n / sample)) finds per query are expected; an overflowing log only loses sharing
+        a.flog_cap = (uint32_t) (pl.R * tc::kTileM) * (uint32_t) std::min(1024, std::max(64, 8 * k));
         L.flog_tail_bytes = ((size_t) pl.G * sizeof(uint32_t) + 255) & ~(size_t) 255;
         L.flog_bytes = (size_t) pl.G * a.flog_cap * sizeof(uint4);
         GP_TRY(reserve(ctx, ctx->flog, L.flog_tail_bytes + L.flog_bytes));
@@ -409,7 +411,8 @@ int tc_sample(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, cudaStream_
         a.sample_pass = 1;
         // no find log in the sample passes: they are bound by the selection warps (a cold pass accepts nearly every record),
         // and sharing would multiply exactly that work by the number of splits (measured: 2.0M -> 5.9M clk for the three levels)
-        a.flog = nullptr;
+        static const bool log_samples = std::getenv("GPANN_TC_LOG_SAMPLE") != nullptr;
+        if (!log_samples) a.flog = nullptr;
         static const char* e_sst = std::getenv("GPANN_TC_STATS");
         if (e_sst && std::atoi(e_sst) >= 2) {
             GP_TRY(reserve(ctx, ctx->misc, 256));

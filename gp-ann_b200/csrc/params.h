@@ -225,7 +225,7 @@ struct Args {
     int mips;                // 1: MIPS build of the scan (distance = 1 - <q,x>, src/dist.cpp:50-52); 0: squared L2
     uint32_t* peer_bound[kMaxPeers];  // sharded calls: the other ranks' `bound` arrays (NVLink peer memory), same slot layout
     int npeers;
-    // Find log (lists_smem plans with S > 1, see topk_tc.cu): the S CTAs that serve a query group append every key they accept
+    // Find log (plans with S > 1, see topk_tc.cu): the S CTAs that serve a query group append every key they accept
     // to the group's log and apply the others' entries to their own lists, so each filters with the running k-th distance
     // of ALL splits instead of its own finds'.  Entries are {key lo, key hi, slot | split << 16, -}, 0xFF-filled = not written.
     uint4* flog;             // [G][flog_cap], nullptr = off
@@ -238,8 +238,7 @@ inline size_t smem_bytes(int R, int kblocks, int stages, int qcap, int lists_sme
     return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
            (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 16 /*queues*/ +
            (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/ +
-           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/ + 64 /*dirty bitmap (peer bounds)*/ +
-           (lists_smem ? (size_t) R * kTileM * 2 : 0) /*own-entry masks of the lists (find log)*/;
+           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/ + 64 /*dirty bitmap (peer bounds)*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {
     const uint32_t fmt = is_signed ? 1u : 0u;

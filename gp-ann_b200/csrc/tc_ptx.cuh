@@ -60,8 +60,27 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 // Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
+#ifndef GPANN_WAIT_OOL
+#define GPANN_WAIT_OOL 0
+#endif
+// The retry loop with its watchdog, out of line (GPANN_WAIT_OOL): the callers' hot loops then fall through a not-taken
+// branch when the first try_wait succeeds instead of jumping over ~25 cold instructions at every hand-off.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xFFu) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
+#if GPANN_WAIT_OOL
+    mbar_wait_slow(bar, parity);
+#else
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -71,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             else if (now - t0 > 4000000000ull) __trap();
         }
     }
+#endif
 }
 // Busy-polling wait (mbarrier.test_wait never suspends the thread): lower wake-up latency than try_wait at the price of
 // issue slots; for the hand-offs on the kernel's critical path (accumulator ready / accumulator slot free).

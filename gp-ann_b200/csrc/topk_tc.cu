@@ -52,6 +52,10 @@
 #ifndef GPANN_LEAN
 #define GPANN_LEAN 0
 #endif
+// 1: the hit test of a chunk pair is a plain (divergent) branch instead of a warp vote + uniform branch
+#ifndef GPANN_NO_VOTE
+#define GPANN_NO_VOTE 0
+#endif
 #ifndef GPANN_SEL_SLEEP
 #define GPANN_SEL_SLEEP 1000
 #endif
@@ -231,20 +235,28 @@ struct SelState {
     uint32_t id_base;
     float eps;
     // find log of this CTA's query group (Args::flog): every accepted key of this CTA is appended, the other splits'
-    // entries are applied to the lists as FOREIGN keys (they tighten the k-th distance but are not part of this CTA's output:
-    // own[qs] marks the list positions that hold this CTA's own finds)
+    // entries are applied to the lists as FOREIGN keys: they tighten the k-th distance but are not this CTA's to report, so
+    // they are stored with the id field set to kInvalidId (>= the real key: the list's k-th stays a valid, at most
+    // tie-conservative bound, and an own key of the true top-k still has fewer than k keys below it) and blanked at the end
     uint4* flog;
     uint32_t* flog_tail;
     uint32_t flog_cap, split;
-    uint16_t* own;
 };
 
-__device__ __forceinline__ void log_find(const SelState& s, uint32_t qs, uint64_t key) {
-    const uint32_t pos = atomicAdd(s.flog_tail, 1u);
-    if (pos < s.flog_cap) {
-        uint4 e = make_uint4((uint32_t) key, (uint32_t) (key >> 32), qs | (s.split << 16), 0u);
-        asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(s.flog + pos), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
-    }
+// Append the keys this warp accepted in one batch to the group's find log: one reservation (global atomic round trip) per
+// batch, one 16-byte store per key.
+__device__ __forceinline__ void log_finds(const SelState& s, bool accepted, uint32_t qs, uint64_t key, int lane) {
+    const unsigned am = __ballot_sync(0xffffffffu, accepted);
+    if (am == 0) return;
+    const int leader = __ffs(am) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(s.flog_tail, (uint32_t) __popc(am));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const uint32_t pos = base + (uint32_t) __popc(am & ((1u << lane) - 1u));
+    if (accepted && pos < s.flog_cap)
+        asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(s.flog + pos), "r"((uint32_t) key), "r"((uint32_t) (key >> 32)),
+                     "r"(qs | (s.split << 16)), "r"(0u)
+                     : "memory");
 }
 
 // Squared L2 distance of two fp32 rows in the reference's summation order (src/dist.cpp:9-16 ->
@@ -306,8 +318,10 @@ __device__ __forceinline__ void publish_threshold(const SelState& s, uint32_t qs
     apply_bound<kFloat, kMips>(s, qs, kd);
     // distances are non-negative, so their bit patterns order like unsigned integers
     if (s.gbound && kd >= 0.f) {
-        const uint32_t bits = __float_as_uint(kd);
-        if (atomicMin(s.gbound + qs, bits) > bits && s.npeers > 0) atomicOr(s.dirty + (qs >> 5), 1u << (qs & 31));
+        // fire and forget (RED.MIN): waiting for the old value cost a global round trip per accepted record.  The dirty bit is set
+        // even when another split already published a smaller bound -- the push to the peers then repeats that value.
+        atomicMin(s.gbound + qs, __float_as_uint(kd));
+        if (s.npeers > 0) atomicOr(s.dirty + (qs >> 5), 1u << (qs & 31));
     }
 }
 // Pull the bounds other point splits have published for this selection warp's queries into the filter thresholds.
@@ -330,7 +344,9 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
 }
 
 template <bool kFloat, bool kMips>
-__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t key, uint32_t extra, bool foreign = false) {
+__device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, uint64_t& key, uint32_t extra, bool& accepted,
+                                              bool foreign = false) {
+    if (foreign) key |= 0xFFFFFFFFull;  // keep the distance, drop the id (see SelState::flog)
     if (kFloat && !foreign) {  // the record holds (accumulator, id) and the point's norm
         const uint32_t id = (uint32_t) key;
         const uint64_t kth_now = s.kth[qs];
@@ -358,20 +374,15 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     int cnt = s.cnt[qs];
     if (s.k <= 32) {
         if (cnt < s.k) {
-            if (s.flog) s.own[qs] = (uint16_t) ((s.own[qs] & ~(1u << cnt)) | (foreign ? 0u : 1u << cnt));
             list[cnt++] = key;
             s.cnt[qs] = cnt;
-            if (cnt < s.k) {
-                if (s.flog && !foreign) log_find(s, qs, key);
-                return false;
-            }
+            accepted = true;
+            if (cnt < s.k) return false;
         } else {
             if (key >= s.kth[qs]) return false;
-            const int mp0 = s.maxpos[qs];
-            list[mp0] = key;
-            if (s.flog) s.own[qs] = (uint16_t) ((s.own[qs] & ~(1u << mp0)) | (foreign ? 0u : 1u << mp0));
+            list[s.maxpos[qs]] = key;
         }
-        if (s.flog && !foreign) log_find(s, qs, key);
+        accepted = true;
         // new maximum of the list: the keys sit in global memory (L2), so the loads are issued eight at a time instead
         // of one dependent load per key (a record cost ~3 us of selection-warp time before, ~1M records per sample pass)
         uint64_t m = 0;
@@ -395,6 +406,7 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
     if (key >= s.kth[qs]) return false;
     list[cnt++] = key;
     s.cnt[qs] = cnt;
+    accepted = true;
     return cnt >= s.cap;
 }
 
@@ -417,7 +429,9 @@ __device__ __forceinline__ void poll_log(const SelState& s, uint32_t& log_read, 
         while (__any_sync(0xffffffffu, pending)) {  // entries for the same query: one per round, lowest lane first
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             if (pending && (__ffs(peers) - 1) == lane) {
-                select_insert<kFloat, kMips>(s, qs, key, 0u, true);
+                uint64_t fkey = key;
+                bool acc = false;
+                select_insert<kFloat, kMips>(s, qs, fkey, 0u, acc, true);
                 pending = false;
             }
             __syncwarp();
@@ -474,12 +488,13 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         clk_pop += (unsigned long long) (c_ins - c_top);
         ++n_batches;
         // records for the same query are applied one per round (lowest lane first)
+        bool accepted = false;  // this lane's record went into its query's list (key then holds the exact key)
         while (__any_sync(0xffffffffu, pending)) {
             ++n_rounds;
             const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
             bool compact = false;
             if (pending && (__ffs(peers) - 1) == lane) {
-                compact = select_insert<kFloat, kMips>(s, qs, key, extra);
+                compact = select_insert<kFloat, kMips>(s, qs, key, extra, accepted);
                 pending = false;
             }
             __syncwarp();
@@ -498,6 +513,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                 __syncwarp();
             }
         }
+        if (s.flog) log_finds(s, accepted, qs, key, lane);
         if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
         // a busy selection warp (cold start) still trades bounds with the other splits / ranks now and then
         ++busy;
@@ -570,8 +586,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int* s_maxpos = s_nq + R * kTileM;
     uint64_t* s_lists = reinterpret_cast<uint64_t*>(s_maxpos + R * kTileM);   // [R*128][kSmemListKeys] when a.lists_smem
     uint32_t* s_dirty = reinterpret_cast<uint32_t*>(s_lists + (a.lists_smem ? (size_t) R * kTileM * kSmemListKeys : 0));  // [R*4]
-    uint16_t* s_own = reinterpret_cast<uint16_t*>(s_dirty + 16);  // [R*128] when a.lists_smem: list positions holding own finds
-    const bool use_flog = a.flog != nullptr && a.lists_smem;
+    const bool use_flog = a.flog != nullptr && a.k <= 32;  // poll_log applies foreign keys without the k > 32 compaction step
 
     const int nslots = R * kTileM;
     const size_t qbase = (size_t) g * nslots;  // first (padded) query handled by this CTA
@@ -579,7 +594,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         s_kth[i] = kEmptyKey;
         s_cnt[i] = 0;
         s_maxpos[i] = 0;
-        if (use_flog) s_own[i] = 0;
         // warm start: an upper bound on this query's kth distance from the sample passes (+inf = none)
         const float b = a.bound ? __uint_as_float(a.bound[qbase + i]) : __int_as_float(0x7f800000);
         // Padding slots (query index >= nq) hold zero vectors: left alone, every low-norm point "beats" their k-th
@@ -1056,7 +1070,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                             tmem_wait_ld();
                             if (c == kColsPerWarp / 64 - 1) {  // accumulator drained into registers: hand the slot back before
                                 tcgen05_fence_before();        // the arithmetic, so a slow-path entry cannot stall the MMA
-                                __syncwarp();
+                                if (!GPANN_NO_VOTE) __syncwarp();  // (tcgen05.wait::ld is warp-wide: nothing to wait for)
                                 if (lane == 0) mbar_arrive(bar_te);
                             }
                         }
@@ -1067,27 +1081,29 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
                                 if (fmaxf(ma, mb) == 3.0e38f) s_U[qs] = __float_as_int(ma);
                                 continue;
                             }
-                            if (__any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
+                            if (GPANN_NO_VOTE ? fmaxf(ma, mb) >= Tf : __any_sync(0xffffffffu, fmaxf(ma, mb) >= Tf)) {
                                 // cold lane of a SAMPLE pass (no bound yet): any subset of real distances bounds the k-th one,
                                 // so only the best value of each chunk goes to the selection warp instead of all 32
                                 const bool cold = sample_pass && Tf < -1.0e37f;
                                 if (ma >= Tf) enqueue_chunk_f(va, cold ? ma : Tf, tn, ti, col0, qs, q);
                                 if (mb >= Tf) enqueue_chunk_f(vb, cold ? mb : Tf, tn, ti, col0 + 32, qs, q);
-                                __syncwarp();
+                                if (!GPANN_NO_VOTE) __syncwarp();
                             }
+                            if (GPANN_NO_VOTE) __syncwarp();  // divergent hit branch: reconverge before the next .aligned load
                         } else {
                             const int ma = max32(va), mb = max32(vb);
                             if (mode == 1 || mode == 3) {
                                 if (max(ma, mb) == 0x7fffffff) s_U[qs] = ma;
                                 continue;
                             }
-                            if (__any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
+                            if (GPANN_NO_VOTE ? max(ma, mb) >= Ti : __any_sync(0xffffffffu, max(ma, mb) >= Ti)) {
                                 ++slow_entries;
                                 const bool cold = sample_pass && Ti < -(1 << 28);  // see the float branch
                                 if (ma >= Ti) enqueue_chunk(va, cold ? ma : Ti, tn, ti, col0, nqraw, qs, q, mips);
                                 if (mb >= Ti) enqueue_chunk(vb, cold ? mb : Ti, tn, ti, col0 + 32, nqraw, qs, q, mips);
-                                __syncwarp();
+                                if (!GPANN_NO_VOTE) __syncwarp();
                             }
+                            if (GPANN_NO_VOTE) __syncwarp();
                         }
                     }
                 }
@@ -1143,7 +1159,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.flog_tail = use_flog ? a.flog_tail + g : nullptr;
         ss.flog_cap = a.flog_cap;
         ss.split = (uint32_t) s;
-        ss.own = s_own;
         if (a.mips) selection_warp_loop<kFloat, true>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         else selection_warp_loop<kFloat, false>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
@@ -1158,7 +1173,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
             const int cnt = s_cnt[qs];
             if (use_flog) {  // the other splits' keys served the threshold only: they are not this CTA's to report
-                if (lane < cnt && !((s_own[qs] >> lane) & 1u)) my_lists[(size_t) qs * lstride + lane] = kEmptyKey;
+                uint64_t* wl = my_lists + (size_t) qs * lstride;
+                for (int j = lane; j < cnt; j += 32)
+                    if ((uint32_t) wl[j] == kInvalidId) wl[j] = kEmptyKey;
                 __syncwarp();
             }
             warp_select_topk_dyn<16>(b, cnt, a.k, dst, lane, min(a.cap, max(32, pow2_ceil(max(cnt, a.k)))));

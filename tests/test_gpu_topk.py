@@ -113,6 +113,34 @@ def test_tensor_paced_splits_bit_exact(ctx, gpann_mod, oracle, monkeypatch):
     assert_topk_exact(d1, i1, d0, i0, c1, c0)
 
 
+def test_tensor_find_log_shares_keys_between_splits_bit_exact(ctx, gpann_mod, oracle, monkeypatch):
+    """k <= 16 with several point splits per query group: the splits append every accepted key to the group's find log
+    and apply each other's entries as foreign keys (id field dropped, blanked before the CTA reports its list).  Heavy
+    ties (binary coordinates, duplicated rows) make the tie-break on ids and the foreign-key ordering matter; the result
+    must be bit-identical to the oracle with the log on and with GPANN_TC_NOLOG."""
+    rng = np.random.default_rng(77)
+    P = rng.integers(0, 2, (60_000, 64)).astype(np.uint8)
+    P[5000:5040] = P[7]           # exact duplicates across different splits (rows are sorted by norm, ids break the ties)
+    P[40_000:40_016] = P[7]
+    Q = np.concatenate([P[:24], rng.integers(0, 2, (276, 64)).astype(np.uint8)]).astype(np.float32)
+    d0, i0, c0 = oracle.ground_truth(P.astype(np.float32), Q, 16)
+    for nolog in (False, True):
+        if nolog:
+            monkeypatch.setenv("GPANN_TC_NOLOG", "1")
+        d1, i1, c1, used = _run(ctx, gpann_mod, P, Q, 16, gpann_mod.ALGO_TENSOR)
+        assert used == "tensor_u8"
+        assert_topk_exact(d1, i1, d0, i0, c1, c0)
+    monkeypatch.delenv("GPANN_TC_NOLOG")
+    # float rows: foreign keys carry exact re-ranked distances
+    Pf = rng.standard_normal((50_000, 48)).astype(np.float32)
+    Qf = rng.standard_normal((200, 48)).astype(np.float32)
+    d1, i1, c1, used = _run(ctx, gpann_mod, Pf, Qf, 10, gpann_mod.ALGO_TENSOR)
+    assert used == "tensor_bf16"
+    d0, i0, c0 = oracle.ground_truth(Pf, Qf, 10)
+    assert np.array_equal(c1, c0)
+    assert_topk_close(d1, i1, d0, i0)
+
+
 def test_tensor_heavy_ties_and_duplicates(ctx, gpann_mod, oracle):
     rng = np.random.default_rng(5)
     P = rng.integers(0, 2, (4000, 128)).astype(np.uint8)
