@@ -228,6 +228,8 @@ struct Args {
     // Find log (plans with S > 1, see topk_tc.cu): the S CTAs that serve a query group append every key they accept
     // to the group's log and apply the others' entries to their own lists, so each filters with the running k-th distance
     // of ALL splits instead of its own finds'.  Entries are {key lo, key hi, slot | split << 16, -}, 0xFF-filled = not written.
+    int interleave;          // 1: split s scans the logical tiles s, s + S, ... (every split sees the whole norm range)
+    uint32_t* qstat;         // [G][S][R*128] order-statistic bounds of the splits (k > 32, topk_tc.cu), 0xFF-filled before the launch
     uint4* flog;             // [G][flog_cap], nullptr = off
     uint32_t* flog_tail;     // [G] entries reserved (zeroed before the launch; may run past flog_cap = dropped)
     uint32_t flog_cap;

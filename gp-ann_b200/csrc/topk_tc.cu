@@ -241,6 +241,13 @@ struct SelState {
     uint4* flog;
     uint32_t* flog_tail;
     uint32_t flog_cap, split;
+    // Order-statistic bound (k > 32, Args::qstat): after every compaction this CTA publishes the distance of its m-th best
+    // key, m = ceil(k / S).  If every split of the group holds m keys at or below t, the group holds at least k: the largest of
+    // the S published values bounds the k-th distance of the union -- far tighter than the smallest per-split k-th distance
+    // once the splits are interleaved (each then sees a 1/S sample of the whole set).
+    uint32_t* qstat_mine;         // [nslots] this split's row (float bits; 0xFFFFFFFF = nothing yet)
+    const uint32_t* qstat_group;  // [S][nslots] all rows of the group
+    int S, qstat_m;
 };
 
 // Append the keys this warp accepted in one batch to the group's find log: one reservation (global atomic round trip) per
@@ -330,6 +337,12 @@ __device__ __forceinline__ void refresh_bounds(const SelState& s, int sel, int l
     if (!s.gbound) return;
     for (int base = sel * 32; base < s.nslots; base += 32 * kSelWarps) {
         const uint32_t qs = (uint32_t) (base + lane);
+        if (s.qstat_group) {  // the union's k-th distance is at most the largest m-th distance of the splits
+            uint32_t worst = 0;
+            for (int j = 0; j < s.S; ++j) worst = max(worst, __ldcg(s.qstat_group + (size_t) j * s.nslots + qs));
+            if (worst < 0x7f800000u && atomicMin(s.gbound + qs, worst) > worst && s.npeers > 0)
+                atomicOr(s.dirty + (qs >> 5), 1u << (qs & 31));
+        }
         const uint32_t bits = __ldcg(s.gbound + qs);
         const float b = __uint_as_float(bits);
         if (b < 3.0e38f) apply_bound<kFloat, kMips>(s, qs, b);
@@ -509,6 +522,10 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
                     s.cnt[qsL] = s.k;
                     s.kth[qsL] = newkth;
                     publish_threshold<kFloat, kMips>(s, qsL, newkth);
+                    if (s.qstat_mine) {
+                        const float dm = key_dist(b[s.qstat_m - 1]);  // the list is sorted ascending now
+                        if (dm >= 0.f) __stcg(s.qstat_mine + qsL, __float_as_uint(dm));
+                    }
                 }
                 __syncwarp();
             }
@@ -517,7 +534,7 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         if (stats) clk_insert += (unsigned long long) (clock64() - c_ins);
         // a busy selection warp (cold start) still trades bounds with the other splits / ranks now and then
         ++busy;
-        if (s.npeers > 0 && (busy & 15u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);
+        if ((s.npeers > 0 || s.qstat_group) && (busy & 15u) == 0) refresh_bounds<kFloat, kMips>(s, sel, lane);
         if ((busy & 3u) == 0) poll_log<kFloat, kMips>(s, log_read, sel, lane);
     }
     if (stats && lane == 0 && sel == 0 && blockIdx.x == 0) {  // diagnostics (GPANN_TC_STATS)
@@ -559,8 +576,12 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     const int R = a.R, KB = a.kblocks, NST = a.stages;
     const int g = blockIdx.x % a.G, s = blockIdx.x / a.G;
     // logical tile indices [tile_begin, tile_end) of this split; physical tile = tile_lo + index * tile_stride
-    const uint32_t tile_begin = (uint32_t) (((uint64_t) a.ntiles * s) / a.S);
-    const uint32_t tile_end = (uint32_t) (((uint64_t) a.ntiles * (s + 1)) / a.S);
+    // (a.interleave: split s takes the logical tiles s, s + S, s + 2S, ... instead of a contiguous range, so every split
+    // sees the whole norm range -- what the order-statistic bound below needs; the loops then count from 0)
+    const uint32_t tile_begin = a.interleave ? 0u : (uint32_t) (((uint64_t) a.ntiles * s) / a.S);
+    const uint32_t tile_end = a.interleave ? (a.ntiles > (uint32_t) s ? (a.ntiles - (uint32_t) s + (uint32_t) a.S - 1u) / (uint32_t) a.S : 0u)
+                                           : (uint32_t) (((uint64_t) a.ntiles * (s + 1)) / a.S);
+    const uint32_t tile_first = a.interleave ? (uint32_t) s : tile_begin, tile_step = a.interleave ? (uint32_t) a.S : 1u;
     const uint32_t q_tile_bytes = (uint32_t) KB * kQBlockBytes, p_tile_bytes = (uint32_t) KB * kPBlockBytes;
 
     // ---- carve shared memory (operand tiles 1024-byte aligned for SWIZZLE_128B) ----
@@ -678,8 +699,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
             long long w_empty = 0;
             const long long t_begin = stats ? clock64() : 0;
             uint32_t st = 0, ph = 0;
-            size_t row0 = ((size_t) a.tile_lo + (size_t) tile_begin * a.tile_stride) * kTileN;
-            const size_t row_step = (size_t) a.tile_stride * kTileN;
+            size_t row0 = ((size_t) a.tile_lo + (size_t) tile_first * a.tile_stride) * kTileN;
+            const size_t row_step = (size_t) tile_step * a.tile_stride * kTileN;
             // Pacing: the G CTAs of a point split stream the same tiles; left alone they drift apart by more than the L2
             // holds and every tile is fetched from HBM ~3.6 times (ncu: 49 GB read for 13.6 GB of points).  Every 32 tiles
             // a CTA publishes its position and waits until the slowest CTA of its split is within kPaceWindow tiles.
@@ -1159,6 +1180,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.flog_tail = use_flog ? a.flog_tail + g : nullptr;
         ss.flog_cap = a.flog_cap;
         ss.split = (uint32_t) s;
+        const bool use_qstat = a.qstat != nullptr && a.k > 32 && a.bound != nullptr;
+        ss.qstat_group = use_qstat ? a.qstat + (size_t) g * a.S * nslots : nullptr;
+        ss.qstat_mine = use_qstat ? a.qstat + ((size_t) g * a.S + s) * nslots : nullptr;
+        ss.S = a.S;
+        ss.qstat_m = (a.k + a.S - 1) / a.S;
         if (a.mips) selection_warp_loop<kFloat, true>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         else selection_warp_loop<kFloat, false>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
