@@ -172,7 +172,14 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     p.qpitch = (p.d + 3) & ~3;
     p.cap = pow2_ceil(k + kStreamTile);
     p.vec_ok = (((uintptr_t) pts->rows + row_begin * pts->pitch) % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
-    const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
+    // two row tiles (the next one in flight behind the scan of this one) when the rows allow 16-byte copies, two tiles leave
+    // room for two CTAs per SM, and the scan is bound by HBM: few queries.  Measured (u8 100M x 128 / f32 10M x 96, one or two
+    // buffers): nq = 1: 4.40 -> 3.09 ms / 1.07 -> 0.93 ms; nq = 4: 7.26 -> 5.48 / 1.69 -> 2.19; nq = 16: 19.0 -> 22.9 / 4.38 -> 5.19
+    // (more queries make the tile compute-bound and the second buffer only costs occupancy).
+    static const bool one_buf = std::getenv("GPANN_STREAM_NBUF1") != nullptr;
+    const size_t nq_hbm_bound = pts->storage == GPANN_STORAGE_F32 ? 1 : 4;
+    p.nbuf = (p.vec_ok && !one_buf && nq <= nq_hbm_bound && (size_t) kStreamTile * p.spitch * 2 <= 104 * 1024) ? 2 : 1;
+    const size_t tile_bytes = (size_t) p.nbuf * kStreamTile * p.spitch;
     // per query: float row, candidate buffer, threshold + count; byte storage adds the query packed as bytes (qpitch bytes,
     // a multiple of 16) + its integer norm + the "integer-valued" flag of the dp4a path
     const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16 + (elem == 1 ? (size_t) ((p.qpitch + 15) & ~15) + 16 : 0);
@@ -498,6 +505,8 @@ int tc_main(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, bool carry, b
         cudaMemcpy(h, ctx->misc.p, 256, cudaMemcpyDeviceToHost);
         const double g = (double) L.grid, items = (double) L.tiles_total / S * pl.R * tc::kHalves;
         std::fprintf(stderr, "[gpann stats] main pass: %llu records pushed, %llu slow-path entries (warp x chunk pair), grid %u, %.0f items/CTA\n", h[0], h[1], L.grid, items);
+        std::fprintf(stderr, "[gpann stats] main pass CTA 0 clk: filter loop done %llu, selection drained %llu, final selection done %llu | slowest CTA: set-up %llu, "
+                             "filter loop %llu, whole kernel %llu clk\n", h[10], h[11], h[12], h[22], h[23], h[21]);
         std::fprintf(stderr, "[gpann stats] clk per item (CTA average): MMA thread total %.0f = wait operands %.0f + wait TMEM slot %.0f + issue %.0f | "
                              "filter warp 0 total %.0f = wait accumulator %.0f + wait tile %.0f + work %.0f | TMA thread total %.0f, wait free stage %.0f\n",
                      h[2] / g / items, h[3] / g / items, h[4] / g / items, (h[2] - h[3] - h[4]) / g / items, h[5] / g / items, h[6] / g / items,

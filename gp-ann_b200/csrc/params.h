@@ -27,6 +27,7 @@ struct StreamParams {
     int spitch;             // shared-memory row pitch in bytes (odd multiple of 16)
     int qpitch;             // shared-memory query pitch in floats (multiple of 4)
     int vec_ok;             // rows can be fetched with 16-byte loads
+    int nbuf;               // row tiles in shared memory: 2 = the next tile is fetched with cp.async while this one is scanned (vec_ok only)
     uint64_t* partial;      // [gridDim.x, nq, k]
     const int* gate;        // optional device flag: the kernel runs only when (*gate != 0) == gate_want (asynchronous fall-backs)
     int gate_want;

@@ -28,8 +28,10 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     const int elem = STORAGE == kF32 ? 4 : 1;
     const int row_bytes = p.d * elem;
 
-    unsigned char* s_rows = smem_raw;                                            // kStreamTile * spitch
-    float* s_q = reinterpret_cast<float*>(s_rows + (size_t) kStreamTile * p.spitch);  // qb * qpitch
+    unsigned char* s_rows0 = smem_raw;                                           // nbuf * kStreamTile * spitch
+    const size_t tile_smem = (size_t) kStreamTile * p.spitch;
+    const int nbuf = p.nbuf > 1 ? 2 : 1;
+    float* s_q = reinterpret_cast<float*>(s_rows0 + (size_t) nbuf * tile_smem);   // qb * qpitch
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(s_q + (size_t) p.qb * p.qpitch);    // qb * cap
     uint64_t* s_thr = s_buf + (size_t) p.qb * p.cap;                              // qb
     int* s_cnt = reinterpret_cast<int*>(s_thr + p.qb);                            // qb
@@ -71,11 +73,34 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
 
     const size_t nrows = p.row_end - p.row_begin;
     const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Double-buffered ring (nbuf == 2): the rows of the CTA's NEXT tile travel HBM -> shared memory with cp.async (16 bytes
+    // each, no register staging) while this tile is scanned; a single-buffered CTA alternates between a load phase and a
+    // compute phase and leaves the memory system idle half of the time (u8 nq = 1: 0.43 of the copy bandwidth).
+    auto fetch_async = [&](size_t tile, unsigned char* dst) {
         const size_t r0 = p.row_begin + tile * kStreamTile;
         const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
         const char* src = p.rows + r0 * p.pitch;
-        if (p.vec_ok) {
+        const int cpr = row_bytes >> 4;
+        for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
+            const int r = idx / cpr, c = idx - r * cpr;
+            const uint32_t d32 = (uint32_t) __cvta_generic_to_shared(dst + (size_t) r * p.spitch + c * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src + (size_t) r * p.pitch + (size_t) c * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (nbuf == 2 && (size_t) blockIdx.x < ntiles) fetch_async(blockIdx.x, s_rows0);
+    int it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const size_t r0 = p.row_begin + tile * kStreamTile;
+        const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
+        const char* src = p.rows + r0 * p.pitch;
+        unsigned char* s_rows = s_rows0 + (nbuf == 2 ? (size_t) (it & 1) * tile_smem : 0);
+        if (nbuf == 2) {
+            // the other buffer was last read two iterations ago (a __syncthreads() closes every iteration)
+            if (tile + gridDim.x < ntiles) fetch_async(tile + gridDim.x, s_rows0 + (size_t) ((it + 1) & 1) * tile_smem);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's group has landed
+        } else if (p.vec_ok) {
             const int cpr = row_bytes >> 4;  // 16-byte chunks per row (row_bytes % 16 == 0 when vec_ok)
             for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
                 const int r = idx / cpr, c = idx - r * cpr;
@@ -163,6 +188,7 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
         uint64_t* dst = p.partial + ((size_t) blockIdx.x * p.nq + (q0 + q)) * p.k;
         warp_select_topk_dyn<32>(b, s_cnt[q], p.k, dst, lane, p.cap);
     }
+    if (nbuf == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // the next query batch reuses the shared-memory buffers
     }
 }
