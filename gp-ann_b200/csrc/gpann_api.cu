@@ -179,6 +179,10 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     static const bool one_buf = std::getenv("GPANN_STREAM_NBUF1") != nullptr;
     const size_t nq_hbm_bound = pts->storage == GPANN_STORAGE_F32 ? 1 : 4;
     p.nbuf = (p.vec_ok && !one_buf && nq <= nq_hbm_bound && (size_t) kStreamTile * p.spitch * 2 <= 104 * 1024) ? 2 : 1;
+    if (const char* e_nb = std::getenv("GPANN_STREAM_NBUF")) {  // experiment knob: ring depth 1..4 (needs 16-byte rows)
+        const int nb = std::atoi(e_nb);
+        if (p.vec_ok && nb >= 1 && nb <= 4 && (size_t) kStreamTile * p.spitch * nb <= 160 * 1024) p.nbuf = nb;
+    }
     const size_t tile_bytes = (size_t) p.nbuf * kStreamTile * p.spitch;
     // per query: float row, candidate buffer, threshold + count; byte storage adds the query packed as bytes (qpitch bytes,
     // a multiple of 16) + its integer norm + the "integer-valued" flag of the dp4a path

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
 
     unsigned char* s_rows0 = smem_raw;                                           // nbuf * kStreamTile * spitch
     const size_t tile_smem = (size_t) kStreamTile * p.spitch;
-    const int nbuf = p.nbuf > 1 ? 2 : 1;
+    const int nbuf = max(1, min(p.nbuf, 4));
     float* s_q = reinterpret_cast<float*>(s_rows0 + (size_t) nbuf * tile_smem);   // qb * qpitch
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(s_q + (size_t) p.qb * p.qpitch);    // qb * cap
     uint64_t* s_thr = s_buf + (size_t) p.qb * p.cap;                              // qb
@@ -88,18 +88,27 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (nbuf == 2 && (size_t) blockIdx.x < ntiles) fetch_async(blockIdx.x, s_rows0);
+    // ring of nbuf tiles, nbuf - 1 of them in flight: one commit group per iteration (an empty one past the end)
+    for (int b = 0; b + 1 < nbuf; ++b) {
+        const size_t t = blockIdx.x + (size_t) b * gridDim.x;
+        if (t < ntiles) fetch_async(t, s_rows0 + (size_t) b * tile_smem);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     int it = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const size_t r0 = p.row_begin + tile * kStreamTile;
         const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
         const char* src = p.rows + r0 * p.pitch;
-        unsigned char* s_rows = s_rows0 + (nbuf == 2 ? (size_t) (it & 1) * tile_smem : 0);
-        if (nbuf == 2) {
-            // the other buffer was last read two iterations ago (a __syncthreads() closes every iteration)
-            if (tile + gridDim.x < ntiles) fetch_async(tile + gridDim.x, s_rows0 + (size_t) ((it + 1) & 1) * tile_smem);
+        unsigned char* s_rows = s_rows0 + (size_t) (it % nbuf) * tile_smem;
+        if (nbuf > 1) {
+            // the buffer refilled now was last read in the previous iteration (a __syncthreads() closes every iteration)
+            const size_t tnext = tile + (size_t) (nbuf - 1) * gridDim.x;
+            if (tnext < ntiles) fetch_async(tnext, s_rows0 + (size_t) ((it + nbuf - 1) % nbuf) * tile_smem);
             else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's group has landed
+            // this tile's group has landed when at most nbuf - 1 younger groups are pending
+            if (nbuf == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else if (nbuf == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else asm volatile("cp.async.wait_group 3;" ::: "memory");
         } else if (p.vec_ok) {
             const int cpr = row_bytes >> 4;  // 16-byte chunks per row (row_bytes % 16 == 0 when vec_ok)
             for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
         uint64_t* dst = p.partial + ((size_t) blockIdx.x * p.nq + (q0 + q)) * p.k;
         warp_select_topk_dyn<32>(b, s_cnt[q], p.k, dst, lane, p.cap);
     }
-    if (nbuf == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (nbuf > 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // the next query batch reuses the shared-memory buffers
     }
 }
