@@ -48,6 +48,7 @@ struct gpann_ctx {
     // grow-only scratch, reused across calls (a ctx is externally synchronised)
     DevBuf pace;
     DevBuf flog;  // find logs of the tensor top-k kernel: [G] tails (256-byte header block per 64) + [G][cap] entries
+    DevBuf qstat; // order-statistic bounds of the point splits: [G][S][R*128]
     DevBuf partial, cand, qrows, qnorm, qf32, bound, flags, dist_out, id_out, cnt_out, qdev, misc, sort_tmp, sort_a, sort_b, sort_c,
         sort_d, segsums, cent, sums, counts, assign, km_cent, km_hn, km_scal, km_partial, km_amb_list, km_amb_info;
     int km_mode = 0;     // GPANN_KM_MODE env: 2 = probe (MMA issue only, results invalid)

@@ -399,10 +399,11 @@ int tc_setup(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, TcLaunch& L)
     a.interleave = e_il ? std::atoi(e_il) != 0 : 1;
     // k > 32 (append + compaction lists): interleaved splits that publish their ceil(k/S)-th best distance
     const bool no_qstat = std::getenv("GPANN_TC_NOQSTAT") != nullptr;
-    if (!no_qstat && k > 32 && L.S > 1 && ctx->tc_mode == 0) {
+    const bool qstat_small = std::getenv("GPANN_TC_QSTAT_SMALL") != nullptr;  // experiment: also for k <= 32 (where ceil(k/S) <= 2)
+    if (!no_qstat && (k > 32 || (qstat_small && (k + L.S - 1) / L.S <= 2)) && L.S > 1 && ctx->tc_mode == 0) {
         L.qstat_bytes = (size_t) pl.G * L.S * pl.R * tc::kTileM * sizeof(uint32_t);
-        GP_TRY(reserve(ctx, ctx->flog, L.qstat_bytes));
-        a.qstat = (uint32_t*) ctx->flog.p;
+        GP_TRY(reserve(ctx, ctx->qstat, L.qstat_bytes));
+        a.qstat = (uint32_t*) ctx->qstat.p;
     }
     return 0;
 }
@@ -1143,7 +1144,7 @@ void sd_destroy(gpann_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();  // asynchronous entry points may still be running on caller streams
     comm_destroy(ctx);
-    DevBuf* bufs[] = { &ctx->pace, &ctx->flog, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
+    DevBuf* bufs[] = { &ctx->pace, &ctx->flog, &ctx->qstat, &ctx->partial, &ctx->cand, &ctx->qrows, &ctx->qnorm, &ctx->qf32, &ctx->bound, &ctx->flags, &ctx->dist_out,
                        &ctx->id_out, &ctx->cnt_out, &ctx->qdev, &ctx->misc, &ctx->sort_tmp, &ctx->sort_a, &ctx->sort_b,
                        &ctx->sort_c, &ctx->sort_d, &ctx->segsums, &ctx->cent, &ctx->sums, &ctx->counts, &ctx->assign,
                        &ctx->km_cent, &ctx->km_hn, &ctx->km_scal, &ctx->km_partial, &ctx->km_amb_list, &ctx->km_amb_info,

@@ -110,11 +110,20 @@ __device__ __forceinline__ uint4 ld_shared_v4_volatile(const void* p) {
     return v;
 }
 
+// The counters and records live in shared memory: explicit .shared instructions (ATOMS / LDS / STS) -- through the generic
+// pointers the compiler emitted ATOM.E / LD.E.STRONG.SYS, the slowest instructions of a candidate record's detour.
+__device__ __forceinline__ uint32_t ld_shared_u32_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __noinline__ void queue_push(const Queue& q, uint64_t key, uint32_t qs, uint32_t extra = 0u) {
-    const uint32_t pos = atomicAdd(q.tail, 1u);
-    if (pos - *q.head >= q.cap) {  // full: wait for the selection warp (rare)
+    const uint32_t tail_s = smem_u32(q.tail), head_s = smem_u32(const_cast<uint32_t*>(q.head));
+    uint32_t pos;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(tail_s) : "memory");
+    if (pos - ld_shared_u32_volatile(head_s) >= q.cap) {  // full: wait for the selection warp (rare)
         const uint64_t t0 = global_timer_ns();
-        while (pos - *q.head >= q.cap) {
+        while (pos - ld_shared_u32_volatile(head_s) >= q.cap) {
             __nanosleep(64);
             if (global_timer_ns() - t0 > 4000000000ull) __trap();
         }
@@ -398,8 +407,9 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         accepted = true;
         // new maximum of the list: the keys sit in global memory (L2), so the loads are issued eight at a time instead
         // of one dependent load per key (a record cost ~3 us of selection-warp time before, ~1M records per sample pass)
-        uint64_t m = 0;
+        uint64_t m = 0, s1 = kEmptyKey, s2 = kEmptyKey;  // the largest and (order-statistic bound) the two smallest keys
         int mp = 0;
+        const bool want_small = s.qstat_mine != nullptr;
         for (int i0 = 0; i0 < s.k; i0 += 8) {
             uint64_t x[8];
 #pragma unroll
@@ -410,10 +420,23 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
                     m = x[j];
                     mp = i0 + j;
                 }
+            if (want_small) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (i0 + j < s.k) {
+                        const uint64_t lo = x[j] < s1 ? x[j] : s1, hi = x[j] < s1 ? s1 : x[j];
+                        s1 = lo;
+                        s2 = hi < s2 ? hi : s2;
+                    }
+            }
         }
         s.kth[qs] = m;
         s.maxpos[qs] = mp;
         publish_threshold<kFloat, kMips>(s, qs, m);
+        if (want_small) {  // k <= 32: qstat_m is 1 or 2 (see the kernel's set-up)
+            const float dm = key_dist(s.qstat_m == 1 ? s1 : s2);
+            if (dm >= 0.f) __stcg(s.qstat_mine + qs, __float_as_uint(dm));
+        }
         return false;
     }
     if (key >= s.kth[qs]) return false;
@@ -1180,11 +1203,15 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.flog_tail = use_flog ? a.flog_tail + g : nullptr;
         ss.flog_cap = a.flog_cap;
         ss.split = (uint32_t) s;
-        const bool use_qstat = a.qstat != nullptr && a.k > 32 && a.bound != nullptr;
+        // order-statistic bound: the append + compaction lists (k > 32) publish at every compaction; the replace-the-maximum
+        // lists (k <= 32) track their two smallest keys, so they take part when ceil(k / S) <= 2 -- and only where the find
+        // log is off (the sample passes): with the log a list holds foreign keys and its order statistics are the group's
+        const int qm = (a.k + a.S - 1) / a.S;
+        const bool use_qstat = a.qstat != nullptr && a.bound != nullptr && (a.k > 32 || (qm <= 2 && !use_flog));
         ss.qstat_group = use_qstat ? a.qstat + (size_t) g * a.S * nslots : nullptr;
         ss.qstat_mine = use_qstat ? a.qstat + ((size_t) g * a.S + s) * nslots : nullptr;
         ss.S = a.S;
-        ss.qstat_m = (a.k + a.S - 1) / a.S;
+        ss.qstat_m = qm;
         if (a.mips) selection_warp_loop<kFloat, true>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         else selection_warp_loop<kFloat, false>(q, ss, s_ctr + 2 * kSelWarps, lane, sel, stats);
         if (stats && lane == 0) atomicAdd(stats, (unsigned long long) *q.tail);  // records pushed to this queue
