@@ -148,6 +148,12 @@ int launch_merge(gpann_ctx* ctx, const uint64_t* keys, size_t parts, size_t nq_s
 
 // The CUDA-core scan of rows [row_begin,row_end) for nq queries.  Queries are served in batches sized so that the per-CTA
 // partial lists stay inside a fixed scratch budget (the reference's ComputeGroundTruth has no limit on nq or k).
+// Rows per shared-memory tile of the one-thread-per-row kernels: kStreamTile (128), fewer when a row is so long that 128 of
+// them would not leave room for the queries / centroids next to them (f32 d > ~190: GIST-960 stages 24 rows, d = 4096 five).
+static int stream_tile_rows(int spitch) {
+    return (int) std::max<size_t>(1, std::min<size_t>(kStreamTile, (size_t) (96 * 1024) / (size_t) spitch));
+}
+
 int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_t row_end, const float* dq, size_t nq, int k,
                 int metric, const TopkOut& out, cudaStream_t st, const int* gate, int gate_want) {
     StreamParams p;
@@ -178,24 +184,25 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     // (more queries make the tile compute-bound and the second buffer only costs occupancy).
     static const bool one_buf = std::getenv("GPANN_STREAM_NBUF1") != nullptr;
     const size_t nq_hbm_bound = pts->storage == GPANN_STORAGE_F32 ? 1 : 4;
-    p.nbuf = (p.vec_ok && !one_buf && nq <= nq_hbm_bound && (size_t) kStreamTile * p.spitch * 2 <= 104 * 1024) ? 2 : 1;
+    p.tile_rows = stream_tile_rows(p.spitch);
+    p.nbuf = (p.vec_ok && !one_buf && nq <= nq_hbm_bound && (size_t) p.tile_rows * p.spitch * 2 <= 104 * 1024) ? 2 : 1;
     if (const char* e_nb = std::getenv("GPANN_STREAM_NBUF")) {  // experiment knob: ring depth 1..4 (needs 16-byte rows)
         const int nb = std::atoi(e_nb);
-        if (p.vec_ok && nb >= 1 && nb <= 4 && (size_t) kStreamTile * p.spitch * nb <= 160 * 1024) p.nbuf = nb;
+        if (p.vec_ok && nb >= 1 && nb <= 4 && (size_t) p.tile_rows * p.spitch * nb <= 160 * 1024) p.nbuf = nb;
     }
-    const size_t tile_bytes = (size_t) p.nbuf * kStreamTile * p.spitch;
+    const size_t tile_bytes = (size_t) p.nbuf * p.tile_rows * p.spitch;
     // per query: float row, candidate buffer, threshold + count; byte storage adds the query packed as bytes (qpitch bytes,
     // a multiple of 16) + its integer norm + the "integer-valued" flag of the dp4a path
     const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16 + (elem == 1 ? (size_t) ((p.qpitch + 15) & ~15) + 16 : 0);
     const size_t budget = 160 * 1024;
     if (tile_bytes + per_q > 200 * 1024)
-        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: d too large for the streaming kernel's shared-memory tile (f32: d <= 384)");
+        return fail(ctx, GPANN_E_UNSUPPORTED, "topk: k too large for the streaming kernel's shared-memory candidate buffers");
     const int qb = (int) std::min<size_t>(std::min<size_t>(nq, 16),
                                           std::max<size_t>(1, (budget > tile_bytes ? budget - tile_bytes : 0) / per_q));
     p.qb = qb;
     const size_t smem = tile_bytes + (size_t) qb * per_q + 16;  // + alignment slack of the packed byte queries
     const size_t nrows = row_end - row_begin;
-    const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
+    const size_t ntiles = (nrows + p.tile_rows - 1) / p.tile_rows;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     unsigned gx = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
     // a gated launch is normally a no-op (every CTA reads the flag and returns): keep its grid, and its scratch, small
@@ -782,8 +789,12 @@ int topk_dispatch(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, siz
     const bool shape_ok = tensor_shape(ctx, pts->storage, pts->d, nq, k, metric, full);
     // small float sets are not worth a layout -- unless a sharded call needs every rank on the same path
     const bool want_tensor = shape_ok && (ctx->algo == GPANN_ALGO_TENSOR || !is_float || pts->n >= 4096 || between);
-    if (want_tensor && is_float && !pts->tensor_tried)  // lazily build the bf16 layout (handle state, not query state)
-        GP_TRY(build_tensor_float(ctx, const_cast<gpann_points*>(pts), st));
+    if (want_tensor && is_float && !pts->tensor_tried) {  // lazily build the bf16 layout (handle state, not query state)
+        const int rc = build_tensor_float(ctx, const_cast<gpann_points*>(pts), st);
+        // AUTO: no memory for the layout means "the exact streaming kernel serves this set", on the first call as on later ones
+        if (rc != 0 && !(ctx->algo == GPANN_ALGO_AUTO && (rc == GPANN_E_OOM || rc == GPANN_E_UNSUPPORTED))) return rc;
+        if (rc != 0) cudaGetLastError();
+    }
     const bool tensor_ok = want_tensor && pts->has_tensor;
     if (ctx->algo == GPANN_ALGO_TENSOR && !tensor_ok)
         return fail(ctx, GPANN_E_UNSUPPORTED, "topk: tensor kernel needs d<=128, full range, k<=448");
@@ -1023,7 +1034,8 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
     p.spitch = odd16_pitch(row_bytes);
     p.qpitch = ((int) pts->d + 3) & ~3;
     p.vec_ok = ((uintptr_t) pts->rows % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
-    const size_t tile_bytes = (size_t) kStreamTile * p.spitch;
+    p.tile_rows = stream_tile_rows(p.spitch);
+    const size_t tile_bytes = (size_t) p.tile_rows * p.spitch;
     const size_t per_c = (size_t) p.qpitch * 4;
     if (tile_bytes + per_c > 200 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "kmeans: d too large");
     const size_t budget = std::max<size_t>(tile_bytes + per_c, 100 * 1024);
@@ -1032,7 +1044,7 @@ int kmeans_assign_device(gpann_ctx* ctx, const gpann_points* pts, const float* d
     p.out_mindist = d_mindist;
     p.alive = d_alive;
     const size_t smem = tile_bytes + (size_t) p.cchunk * per_c;
-    const size_t ntiles = (pts->n + kStreamTile - 1) / kStreamTile;
+    const size_t ntiles = (pts->n + p.tile_rows - 1) / p.tile_rows;
     const int occ = (int) std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const unsigned grid = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * occ));
     launch_kmeans_assign(p, grid, smem, st);
@@ -1680,9 +1692,10 @@ int objective_device(gpann_ctx* ctx, const gpann_points* pts, const float* d_cen
     const int row_bytes = (int) d * elem;
     p.spitch = odd16_pitch(row_bytes);
     p.vec_ok = ((uintptr_t) pts->rows % 16 == 0) && (pts->pitch % 16 == 0) && (row_bytes % 16 == 0);
-    const size_t smem = (size_t) kStreamTile * p.spitch;
+    p.tile_rows = stream_tile_rows(p.spitch);
+    const size_t smem = (size_t) p.tile_rows * p.spitch;
     if (smem > 200 * 1024) return fail(ctx, GPANN_E_UNSUPPORTED, "objective: d too large");
-    const size_t ntiles = (n + kStreamTile - 1) / kStreamTile;
+    const size_t ntiles = (n + p.tile_rows - 1) / p.tile_rows;
     const unsigned grid = (unsigned) std::max<size_t>(1, std::min<size_t>(ntiles, (size_t) ctx->num_sms * 4));
     GP_TRY(reserve(ctx, ctx->misc, (size_t) grid * 8 + 64));
     p.block_sums = (double*) ctx->misc.p;

@@ -45,11 +45,12 @@ __global__ void __launch_bounds__(kStreamTile) kmeans_assign_kernel(const Assign
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     unsigned char* s_rows = smem_raw;
-    float* s_c = reinterpret_cast<float*>(s_rows + (size_t) kStreamTile * p.spitch);  // cchunk * qpitch
-    const size_t ntiles = (p.pts.n + kStreamTile - 1) / kStreamTile;
+    const int trows = p.tile_rows;
+    float* s_c = reinterpret_cast<float*>(s_rows + (size_t) trows * p.spitch);  // cchunk * qpitch
+    const size_t ntiles = (p.pts.n + trows - 1) / trows;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t r0 = tile * kStreamTile;
-        const int rows_here = (int) min((size_t) kStreamTile, p.pts.n - r0);
+        const size_t r0 = tile * trows;
+        const int rows_here = (int) min((size_t) trows, p.pts.n - r0);
         __syncthreads();
         stage_rows<STORAGE>(p.pts, r0, rows_here, s_rows, p.spitch, p.vec_ok, tid, kStreamTile);
         int best = -1;
@@ -377,10 +378,11 @@ __global__ void __launch_bounds__(kStreamTile) objective_kernel(const ObjectiveP
     const int tid = threadIdx.x;
     unsigned char* s_rows = smem_raw;
     double acc = 0.0;
-    const size_t ntiles = (p.pts.n + kStreamTile - 1) / kStreamTile;
+    const int trows = p.tile_rows;
+    const size_t ntiles = (p.pts.n + trows - 1) / trows;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t r0 = tile * kStreamTile;
-        const int rows_here = (int) min((size_t) kStreamTile, p.pts.n - r0);
+        const size_t r0 = tile * trows;
+        const int rows_here = (int) min((size_t) trows, p.pts.n - r0);
         __syncthreads();
         stage_rows<STORAGE>(p.pts, r0, rows_here, s_rows, p.spitch, p.vec_ok, tid, kStreamTile);
         __syncthreads();

@@ -27,6 +27,7 @@ struct StreamParams {
     int spitch;             // shared-memory row pitch in bytes (odd multiple of 16)
     int qpitch;             // shared-memory query pitch in floats (multiple of 4)
     int vec_ok;             // rows can be fetched with 16-byte loads
+    int tile_rows;          // rows per shared-memory tile (<= kStreamTile; fewer when a row is long: f32 d > ~380)
     int nbuf;               // row tiles in shared memory: 2 = the next tile is fetched with cp.async while this one is scanned (vec_ok only)
     uint64_t* partial;      // [gridDim.x, nq, k]
     const int* gate;        // optional device flag: the kernel runs only when (*gate != 0) == gate_want (asynchronous fall-backs)
@@ -112,6 +113,7 @@ struct AssignParams {
     int kc, metric;
     int cchunk;              // centroids staged per shared-memory chunk
     int spitch, qpitch, vec_ok;
+    int tile_rows;           // rows per shared-memory tile (<= kStreamTile)
     int32_t* out_assign;     // [n]
     float* out_mindist;      // optional [n]
     const unsigned char* alive;  // optional [kc]: centroids with alive[c] == 0 are skipped (clusters removed by an earlier
@@ -136,6 +138,7 @@ struct ObjectiveParams {
     const float* centroids;
     const int32_t* assign;
     int kc, metric, spitch, vec_ok;
+    int tile_rows;       // rows per shared-memory tile (<= kStreamTile)
     double* block_sums;  // [gridDim.x]
 };
 

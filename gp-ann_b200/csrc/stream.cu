@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     const int row_bytes = p.d * elem;
 
     unsigned char* s_rows0 = smem_raw;                                           // nbuf * kStreamTile * spitch
-    const size_t tile_smem = (size_t) kStreamTile * p.spitch;
+    const int trows = p.tile_rows;  // rows per tile: kStreamTile unless a row is too long for 128 of them in shared memory
+    const size_t tile_smem = (size_t) trows * p.spitch;
     const int nbuf = max(1, min(p.nbuf, 4));
     float* s_q = reinterpret_cast<float*>(s_rows0 + (size_t) nbuf * tile_smem);   // qb * qpitch
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(s_q + (size_t) p.qb * p.qpitch);    // qb * cap
@@ -42,7 +43,9 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     int* s_qint = s_qn + p.qb;                                                    // qb: 1 = integer-valued in range
     unsigned char* s_qb = reinterpret_cast<unsigned char*>(                       // qb * qbpitch, 16-byte aligned
         (reinterpret_cast<uintptr_t>(s_qint + p.qb) + 15) & ~(uintptr_t) 15);
-    const bool int_path = STORAGE != kF32 && p.metric == kL2;
+    // ... as long as every partial sum of the reference's float arithmetic is an integer below 2^24 (d * 255^2, d * 128^2):
+    // longer rows round inside the reference's accumulators, and only its own float order reproduces that
+    const bool int_path = STORAGE != kF32 && p.metric == kL2 && p.d <= (STORAGE == kS8 ? 1023 : 258);
 
     for (int i = tid; i < nqb * p.d; i += kStreamTile) {
         const int q = i / p.d, j = i - q * p.d;
@@ -72,13 +75,13 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     }
 
     const size_t nrows = p.row_end - p.row_begin;
-    const size_t ntiles = (nrows + kStreamTile - 1) / kStreamTile;
+    const size_t ntiles = (nrows + trows - 1) / trows;
     // Double-buffered ring (nbuf == 2): the rows of the CTA's NEXT tile travel HBM -> shared memory with cp.async (16 bytes
     // each, no register staging) while this tile is scanned; a single-buffered CTA alternates between a load phase and a
     // compute phase and leaves the memory system idle half of the time (u8 nq = 1: 0.43 of the copy bandwidth).
     auto fetch_async = [&](size_t tile, unsigned char* dst) {
-        const size_t r0 = p.row_begin + tile * kStreamTile;
-        const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
+        const size_t r0 = p.row_begin + tile * trows;
+        const int rows_here = (int) min((size_t) trows, p.row_end - r0);
         const char* src = p.rows + r0 * p.pitch;
         const int cpr = row_bytes >> 4;
         for (int idx = tid; idx < rows_here * cpr; idx += kStreamTile) {
@@ -96,8 +99,8 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     }
     int it = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const size_t r0 = p.row_begin + tile * kStreamTile;
-        const int rows_here = (int) min((size_t) kStreamTile, p.row_end - r0);
+        const size_t r0 = p.row_begin + tile * trows;
+        const int rows_here = (int) min((size_t) trows, p.row_end - r0);
         const char* src = p.rows + r0 * p.pitch;
         unsigned char* s_rows = s_rows0 + (size_t) (it % nbuf) * tile_smem;
         if (nbuf > 1) {

@@ -88,7 +88,9 @@ uint64_t gpann_last_ambiguous(gpann_ctx* ctx);
 
 /* ---- point sets: replaces PointSet (src/defs.h:10-21) as the scanned operand --------------------------- */
 /* Upload n rows of d floats (row-major, as PointSet::coordinates).  Ids reported by gpann_topk are
- * id_base + row index (id_base lets a caller shard rows across devices/processes and keep global ids). */
+ * id_base + row index (id_base lets a caller shard rows across devices/processes and keep global ids).
+ * 1 <= d <= 4096.  The tensor kernels serve d <= 128; longer rows take the exact CUDA-core kernels, which stage fewer rows
+ * per shared-memory tile as d grows (f32 d = 960: 24 rows instead of 128 -- correct, and slower per row). */
 int gpann_points_upload(gpann_ctx* ctx, const float* host_rows, size_t n, size_t d, int storage, uint32_t id_base,
                         gpann_points** out);
 /* Byte rows as stored in .u8bin / .i8bin files (src/points_io.cpp:63-111 without the float widening). */

@@ -221,6 +221,40 @@ def test_edge_cases(ctx, gpann_mod, oracle):
     assert np.array_equal(i2, i0 + 1000)
 
 
+def test_long_rows_use_shorter_tiles(ctx, gpann_mod, oracle):
+    """Rows too long for 128 of them in shared memory (GIST-960, d = 2000, d = 4096 f32; long byte rows): the one-thread-per-row
+    kernels stage fewer rows per tile instead of refusing -- top-k, nearest centroids and the objective against the oracle."""
+    rng = np.random.default_rng(960)
+    for d, n, nq in ((960, 3000, 9), (2000, 700, 5), (4096, 300, 3)):
+        P = rng.standard_normal((n, d)).astype(np.float32)
+        Q = rng.standard_normal((nq, d)).astype(np.float32)
+        pts = ctx.upload(P)
+        try:
+            d1, i1, c1 = ctx.topk(pts, Q, 10)
+            assert ctx.last_algo == "stream"
+            d0, i0, c0 = oracle.ground_truth(P, Q, 10)
+            assert np.array_equal(c1, c0)
+            assert_topk_close(d1, i1, d0, i0)
+            C = P[rng.choice(n, 17, replace=False)].copy()
+            a1 = ctx.kmeans_assign(pts, C)
+            a0, _ = oracle.nearest_centers(P, C)
+            assert np.array_equal(a1, a0)
+            o1 = ctx.objective(pts, C, a1)
+            o0 = oracle.objective(P, C, a1)
+            assert abs(o1 - o0) <= 1e-5 * abs(o0)
+        finally:
+            pts.free()
+    Pb = rng.integers(0, 256, (2500, 3000)).astype(np.uint8)  # byte rows of 3000: exact integers
+    Qb = rng.integers(0, 256, (6, 3000)).astype(np.float32)
+    pts = ctx.upload(Pb)
+    try:
+        d1, i1, c1 = ctx.topk(pts, Qb, 5)
+        d0, i0, c0 = oracle.ground_truth(Pb.astype(np.float32), Qb, 5)
+        assert_topk_exact(d1, i1, d0, i0, c1, c0)
+    finally:
+        pts.free()
+
+
 # ---- properties at sizes the oracle cannot reach quickly -----------------------------------------------------------
 def test_large_tensor_properties(ctx, gpann_mod, oracle, ref):
     rng = np.random.default_rng(77)
