@@ -193,7 +193,8 @@ int topk_stream(gpann_ctx* ctx, const gpann_points* pts, size_t row_begin, size_
     const size_t tile_bytes = (size_t) p.nbuf * p.tile_rows * p.spitch;
     // per query: float row, candidate buffer, threshold + count; byte storage adds the query packed as bytes (qpitch bytes,
     // a multiple of 16) + its integer norm + the "integer-valued" flag of the dp4a path
-    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 16 + (elem == 1 ? (size_t) ((p.qpitch + 15) & ~15) + 16 : 0);
+    // (threshold 8 + count 4 + integer norm 4 + integer flag 4 bytes per query, whatever the storage: the kernel initialises all)
+    const size_t per_q = (size_t) p.qpitch * 4 + (size_t) p.cap * 8 + 24 + (elem == 1 ? (size_t) ((p.qpitch + 15) & ~15) + 16 : 0);
     const size_t budget = 160 * 1024;
     if (tile_bytes + per_q > 200 * 1024)
         return fail(ctx, GPANN_E_UNSUPPORTED, "topk: k too large for the streaming kernel's shared-memory candidate buffers");
