@@ -244,7 +244,8 @@ inline size_t smem_bytes(int R, int kblocks, int stages, int qcap, int lists_sme
     return 1024 + (size_t) R * kblocks * kQBlockBytes + (size_t) stages * kblocks * kPBlockBytes + 256 /*barriers, counters*/ +
            (size_t) stages * kTileN * 8 /*norms+ids per stage*/ + (size_t) kSelWarps * qcap * 16 /*queues*/ +
            (size_t) R * kTileM * (8 + 4 + 4 + 4 + 4) /*per-query selection state*/ +
-           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/ + 64 /*dirty bitmap (peer bounds)*/;
+           (lists_smem ? (size_t) R * kTileM * kSmemListKeys * 8 : 0) /*per-query top-k lists*/ + 64 /*dirty bitmap (peer bounds)*/ +
+           (size_t) R * kTileM /*claim bytes: which lane of a selection batch applies a query's record this round*/;
 }
 inline uint32_t make_idesc_i8(bool is_signed) {
     const uint32_t fmt = is_signed ? 1u : 0u;

@@ -254,6 +254,7 @@ struct SelState {
     // key, m = ceil(k / S).  If every split of the group holds m keys at or below t, the group holds at least k: the largest of
     // the S published values bounds the k-th distance of the union -- far tighter than the smallest per-split k-th distance
     // once the splits are interleaved (each then sees a 1/S sample of the whole set).
+    unsigned char* claim;         // [nslots] shared memory: lane that applies this query's record in the current round
     uint32_t* qstat_mine;         // [nslots] this split's row (float bits; 0xFFFFFFFF = nothing yet)
     const uint32_t* qstat_group;  // [S][nslots] all rows of the group
     int S, qstat_m;
@@ -410,6 +411,32 @@ __device__ __forceinline__ bool select_insert(const SelState& s, uint32_t qs, ui
         uint64_t m = 0, s1 = kEmptyKey, s2 = kEmptyKey;  // the largest and (order-statistic bound) the two smallest keys
         int mp = 0;
         const bool want_small = s.qstat_mine != nullptr;
+        if (!want_small) {
+            // maximum + position as a tournament over 16 keys at a time: all loads in flight at once and a dependent chain of
+            // 4 compare/select levels instead of 16 (this scan is most of what an accepted record costs a selection warp)
+            for (int i0 = 0; i0 < s.k; i0 += 16) {
+                uint64_t v[16];
+                int pos[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    v[j] = (i0 + j < s.k) ? list[i0 + j] : 0ull;
+                    pos[j] = i0 + j;
+                }
+#pragma unroll
+                for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < w; ++j) {
+                        const bool g = v[j + w] > v[j];
+                        v[j] = g ? v[j + w] : v[j];
+                        pos[j] = g ? pos[j + w] : pos[j];
+                    }
+                }
+                if (v[0] >= m) {
+                    m = v[0];
+                    mp = pos[0];
+                }
+            }
+        } else
         for (int i0 = 0; i0 < s.k; i0 += 8) {
             uint64_t x[8];
 #pragma unroll
@@ -527,9 +554,14 @@ __device__ __noinline__ void selection_warp_loop(const Queue q, const SelState s
         bool accepted = false;  // this lane's record went into its query's list (key then holds the exact key)
         while (__any_sync(0xffffffffu, pending)) {
             ++n_rounds;
-            const unsigned peers = __match_any_sync(0xffffffffu, pending ? qs : 0xFFFF0000u + lane);
+            // records of the same query are applied one per round: every pending lane writes its lane id into the query's claim
+            // byte and the lane that reads its own id back goes (MATCH.ANY here cost ~18 % of a busy selection warp's time)
+            volatile unsigned char* claim = s.claim;
+            if (pending) claim[qs] = (unsigned char) lane;
+            __syncwarp();
+            const bool mine = pending && claim[qs] == (unsigned char) lane;
             bool compact = false;
-            if (pending && (__ffs(peers) - 1) == lane) {
+            if (mine) {
                 compact = select_insert<kFloat, kMips>(s, qs, key, extra, accepted);
                 pending = false;
             }
@@ -630,6 +662,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     int* s_maxpos = s_nq + R * kTileM;
     uint64_t* s_lists = reinterpret_cast<uint64_t*>(s_maxpos + R * kTileM);   // [R*128][kSmemListKeys] when a.lists_smem
     uint32_t* s_dirty = reinterpret_cast<uint32_t*>(s_lists + (a.lists_smem ? (size_t) R * kTileM * kSmemListKeys : 0));  // [R*4]
+    unsigned char* s_claim = reinterpret_cast<unsigned char*>(s_dirty + 16);  // [R*128]
     const bool use_flog = a.flog != nullptr && a.k <= 32;  // poll_log applies foreign keys without the k > 32 compaction step
 
     const int nslots = R * kTileM;
@@ -1198,6 +1231,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
         ss.npeers = a.bound ? a.npeers : 0;
         for (int pi = 0; pi < kMaxPeers; ++pi) ss.peer[pi] = pi < a.npeers ? a.peer_bound[pi] + qbase : nullptr;
         ss.dirty = s_dirty;
+        ss.claim = s_claim;
         ss.nslots = nslots;
         ss.flog = use_flog ? a.flog + (size_t) g * a.flog_cap : nullptr;
         ss.flog_tail = use_flog ? a.flog_tail + g : nullptr;
