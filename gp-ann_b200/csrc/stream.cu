@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kStreamTile, 5) topk_stream_kernel(const Strea
     }
 }
 
-// Merge `parts` ascending key lists per query into the k smallest.  One warp per query; keys [parts, nq, k].
+// Merge `parts` key lists per query (k keys each, any order, kEmptyKey = none) into the k smallest.  One warp per query; keys [parts, nq, k].
 // Output: any of out_dist [nq,k] (float), out_id [nq,k], out_keys [nq,k], out_count [nq], out_kth [nq] (the
 // reference's Top().first: the largest kept distance).
 __global__ void __launch_bounds__(128) merge_keys_kernel(const MergeParams p) {

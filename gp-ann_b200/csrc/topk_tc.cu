@@ -1255,6 +1255,18 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
     if (warp >= kFilterWarp0 && warp < kFilterWarp0 + kEpiWarps + kSelWarps) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * (kEpiWarps + kSelWarps)) : "memory");
         if (stats && tid == kFilterWarp0 * 32 && blockIdx.x == 0) stats[11] = (unsigned long long) (clock64() - t_kernel0);  // selection warps drained
+        if (a.k <= 32) {
+            // replace-the-maximum lists hold at most k keys: they go out as they are (unsorted, foreign keys and free positions
+            // as kEmptyKey) -- merge_keys_kernel selects, and a sort per query here cost ~2k clk x 51 queries per warp, most
+            // of what a sample pass spends after its last tile
+            const int t0 = (warp - kFilterWarp0) * 32 + lane, nthr = 32 * (kEpiWarps + kSelWarps);
+            for (int i = t0; i < nslots * a.k; i += nthr) {
+                const int qs = i / a.k, j = i - qs * a.k;
+                uint64_t v = j < s_cnt[qs] ? my_lists[(size_t) qs * lstride + j] : kEmptyKey;
+                if (use_flog && (uint32_t) v == kInvalidId) v = kEmptyKey;  // the other splits' keys served the threshold only
+                a.partial[((size_t) s * a.G * nslots + qbase + qs) * a.k + j] = v;
+            }
+        } else
         for (int qs = warp - kFilterWarp0; qs < nslots; qs += kEpiWarps + kSelWarps) {
             const uint64_t* b = my_lists + (size_t) qs * lstride;
             uint64_t* dst = a.partial + ((size_t) s * a.G * nslots + qbase + qs) * a.k;
