@@ -33,7 +33,19 @@
 //                                   column half (w-2)/4 (128 columns): tcgen05.ld 32x32b.x32 x2, max3 tree, one
 //                                   compare per 64 values.  They hold no per-query state (read-only thresholds).
 //   warps 10..11  : selection    -- one candidate queue each; exact top-k lists in global memory (L2), thresholds in smem
-// Grid: G query groups (R Q-tiles of 128 queries, resident in shared memory) x S point splits.
+// Grid: G query groups (R Q-tiles of 128 queries, resident in shared memory) x S point splits; split s scans the tiles
+// s, s + S, ... (Args::interleave), so every split sees the whole norm range and the candidate records spread evenly.
+//
+// Sharing between the S CTAs of a query group (a CTA that only knows its own finds lets ~S times the candidates through,
+// and with two accumulator slots every candidate record is a detour the MMA issuer ends up waiting for):
+//   * every CTA publishes its k-th distance with atomicMin into Args::bound (and, in a sharded call, into the other GPUs'
+//     bound arrays over NVLink);
+//   * k <= 16: the FIND LOG (Args::flog) -- accepted keys are appended to the group's log and applied by the other CTAs as
+//     foreign keys (distance kept, id dropped, blanked before the CTA reports), so each list tracks the group's running
+//     k-th distance; main pass only (SelState::flog);
+//   * k > 32: an ORDER-STATISTIC bound (Args::qstat) -- each CTA publishes its ceil(k/S)-th best distance at every
+//     compaction, the largest of the S values bounds the union's k-th distance (SelState::qstat_*).
+// For k <= 32 a CTA hands its (unsorted) lists to merge_keys_kernel; larger k selects its k best first.
 #include "common.cuh"
 #include "params.h"
 #include "tc_ptx.cuh"
