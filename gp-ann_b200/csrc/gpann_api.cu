@@ -431,12 +431,12 @@ int tc_sample(gpann_ctx* ctx, const TcPlan& pl, const TcLayout& lay, cudaStream_
     const uint32_t per_split_tiles = L.tiles_total / (uint32_t) S;
     uint32_t l3 = std::min(160u, per_split_tiles / 96u);
     if (l3 < 24u) l3 = 0;  // small splits: two levels (measured: a third costs more than it saves at 1M points)
-    uint32_t levels[3] = { 1, l3 ? std::max(4u, std::min(12u, l3 / 12u)) : 12u, l3 };
+    uint32_t levels[4] = { 1, l3 ? std::max(4u, std::min(12u, l3 / 12u)) : 12u, l3, 0 };  // (a fourth level: experiments only)
     // float rows: every record of a cold pass costs an exact re-rank from HBM, and a cold second level costs no more than a
     // cold first one (C1: 7.3 -> 6.3 ms without the 1-tile level)
     if (pl.is_float) levels[0] = 0;
     const char* e_lv = std::getenv("GPANN_TC_LEVELS");  // experiment / test knob: "a/b/c" tiles per split (0 = skip the level)
-    if (e_lv) std::sscanf(e_lv, "%u/%u/%u", &levels[0], &levels[1], &levels[2]);
+    if (e_lv) std::sscanf(e_lv, "%u/%u/%u/%u", &levels[0], &levels[1], &levels[2], &levels[3]);
     for (uint32_t per_split : levels) {
         if (per_split == 0) continue;
         const uint32_t nsample = (uint32_t) S * per_split;
